@@ -1,0 +1,27 @@
+"""fabe13_b200 -- B200-native (sm_100a) FP64 array sincos behind the FABE13 C API.
+
+The product is libfabe13.so (fabe13_b200/lib/, built from fabe13_b200/csrc/ by fabe13_b200/build.py); this package
+is its ctypes binding.  See DESIGN.md and INTEGRATION.md.
+"""
+from ._lib import Fabe13Error  # noqa: F401
+from .api import (  # noqa: F401
+    CORE_POLY,
+    CORE_PSI,
+    PinnedArray,
+    cos,
+    cot,
+    fill_loguniform_device,
+    fill_uniform_device,
+    get_option,
+    host_core,
+    implementation_name,
+    set_option,
+    shard_bounds,
+    simd_width,
+    sin,
+    sinc,
+    sincos,
+    sincos_k,
+    sincos_legacy,
+    tan,
+)

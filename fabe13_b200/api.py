@@ -1,0 +1,203 @@
+"""Python face of the C ABI: array sincos on host arrays (numpy) or device tensors (torch.cuda), scalar functions,
+options and the slice-sharding helper.  Everything forwards to libfabe13.so; nothing is computed in Python."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+CORE_POLY = 0
+CORE_PSI = 1
+
+
+def _is_torch(x):
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _check_f64(x, name):
+    if _is_torch(x):
+        import torch
+
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            raise TypeError(f"{name} must be a contiguous float64 tensor")
+    else:
+        if x.dtype != np.float64 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{name} must be a C-contiguous float64 array")
+
+
+def _ptr(x):
+    return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+
+def _numel(x):
+    return x.numel() if _is_torch(x) else x.size
+
+
+def sincos(x, out_sin=None, out_cos=None, stream=None):
+    """(sin(x), cos(x)) element-wise for a float64 array.
+
+    torch CUDA tensor -> fabe13_sincos_device on the tensor's device and torch's current stream (asynchronous);
+    numpy array / torch CPU tensor -> fabe13_sincos_host (synchronous; pinned memory takes the direct-copy path).
+    """
+    lib = _lib.load()
+    _check_f64(x, "x")
+    if _is_torch(x):
+        import torch
+
+        s = torch.empty_like(x) if out_sin is None else out_sin
+        c = torch.empty_like(x) if out_cos is None else out_cos
+        _check_f64(s, "out_sin")
+        _check_f64(c, "out_cos")
+        if x.is_cuda:
+            with torch.cuda.device(x.device):
+                st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+                rc = lib.fabe13_sincos_device(x.data_ptr(), s.data_ptr(), c.data_ptr(), x.numel(), st)
+            _lib.check(rc, "fabe13_sincos_device")
+            return s, c
+        rc = lib.fabe13_sincos_host(x.data_ptr(), s.data_ptr(), c.data_ptr(), x.numel())
+        _lib.check(rc, "fabe13_sincos_host")
+        return s, c
+    s = np.empty_like(x) if out_sin is None else out_sin
+    c = np.empty_like(x) if out_cos is None else out_cos
+    _check_f64(s, "out_sin")
+    _check_f64(c, "out_cos")
+    rc = lib.fabe13_sincos_host(x.ctypes.data, s.ctypes.data, c.ctypes.data, x.size)
+    _lib.check(rc, "fabe13_sincos_host")
+    return s, c
+
+
+def sincos_k(x):
+    """(sin, cos, k) for a torch CUDA float64 tensor; k is the reference's quadrant index (test hook)."""
+    import torch
+
+    lib = _lib.load()
+    _check_f64(x, "x")
+    if not (_is_torch(x) and x.is_cuda):
+        raise TypeError("sincos_k needs a CUDA tensor")
+    s = torch.empty_like(x)
+    c = torch.empty_like(x)
+    k = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.fabe13_sincos_device_k(x.data_ptr(), s.data_ptr(), c.data_ptr(), k.data_ptr(), x.numel(), st)
+    _lib.check(rc, "fabe13_sincos_device_k")
+    return s, c, k
+
+
+def sincos_legacy(x, s, c):
+    """The reference's own entry point, void fabe13_sincos(in, sin_out, cos_out, int n), on host or device memory."""
+    lib = _lib.load()
+    lib.fabe13_cuda_clear_error()
+    lib.fabe13_sincos(_ptr(x), _ptr(s), _ptr(c), _numel(x))
+    _lib.check(lib.fabe13_cuda_last_error(), "fabe13_sincos")
+
+
+def sin(x):
+    return _lib.load().fabe13_sin(float(x))
+
+
+def cos(x):
+    return _lib.load().fabe13_cos(float(x))
+
+
+def sinc(x):
+    return _lib.load().fabe13_sinc(float(x))
+
+
+def tan(x):
+    return _lib.load().fabe13_tan(float(x))
+
+
+def cot(x):
+    return _lib.load().fabe13_cot(float(x))
+
+
+def implementation_name():
+    return _lib.load().fabe13_get_active_implementation_name().decode()
+
+
+def simd_width():
+    return _lib.load().fabe13_get_active_simd_width()
+
+
+def set_option(key, value):
+    rc = _lib.load().fabe13_cuda_set_option(key.encode(), int(value))
+    if rc != 0:
+        raise ValueError(f"fabe13_cuda_set_option({key!r}, {value}) rejected (rc={rc})")
+
+
+def get_option(key):
+    v = ctypes.c_longlong(0)
+    rc = _lib.load().fabe13_cuda_get_option(key.encode(), ctypes.byref(v))
+    if rc != 0:
+        raise KeyError(key)
+    return v.value
+
+
+def shard_bounds(n, world, rank):
+    """[begin, end) of the contiguous slice `rank` owns; interior cuts are multiples of 4 elements (32 bytes)."""
+    b = ctypes.c_size_t(0)
+    e = ctypes.c_size_t(0)
+    _lib.load().fabe13_shard_bounds(n, world, rank, ctypes.byref(b), ctypes.byref(e))
+    return b.value, e.value
+
+
+class PinnedArray:
+    """A float64 numpy array in page-locked host memory from fabe13_cuda_host_alloc (fast host path)."""
+
+    def __init__(self, n):
+        lib = _lib.load()
+        self._lib = lib
+        self._p = lib.fabe13_cuda_host_alloc(max(int(n), 1) * 8)
+        if not self._p:
+            raise MemoryError(f"fabe13_cuda_host_alloc({n * 8}) failed")
+        buf = (ctypes.c_double * int(n)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=int(n))
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._lib.fabe13_cuda_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fill_uniform_device(t, seed, lo, hi, first_index=0):
+    """Bench/test hook: fill a CUDA float64 tensor with the synthetic uniform inputs of SURVEY.md section 8d
+    (bit-identical to oracle fabe13_oracle_fill_uniform)."""
+    import torch
+
+    lib = _lib.load()
+    with torch.cuda.device(t.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.fabe13_debug_fill_uniform_device(t.data_ptr(), t.numel(), seed, first_index, lo, hi, st)
+    _lib.check(rc, "fabe13_debug_fill_uniform_device")
+    return t
+
+
+def fill_loguniform_device(t, seed, first_index=0):
+    """Bench/test hook: |x| log-uniform over [1, 2^1024) with random sign (BASELINE config 4)."""
+    import torch
+
+    lib = _lib.load()
+    with torch.cuda.device(t.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.fabe13_debug_fill_loguniform_device(t.data_ptr(), t.numel(), seed, first_index, st)
+    _lib.check(rc, "fabe13_debug_fill_loguniform_device")
+    return t
+
+
+def host_core(x, core=CORE_POLY):
+    """Test hook: the shared per-element core evaluated on the host (fabe13_debug_host_core). Not a product path."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    k = np.empty(x.shape, dtype=np.int64)
+    lib.fabe13_debug_host_core(x.ctypes.data, s.ctypes.data, c.ctypes.data, k.ctypes.data, x.size, core)
+    return s, c, k

@@ -1,0 +1,61 @@
+"""Build libfabe13.so (the C-ABI library with the sm_100a kernels) in-tree with nvcc.
+
+The .so lands in fabe13_b200/lib/ so that it travels with the repository snapshot to the GPU box; nothing is
+JIT-compiled at import time.  `python -m fabe13_b200.build` rebuilds it.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIBPATH = os.path.join(LIBDIR, "libfabe13.so")
+
+SOURCES = ["fabe13_kernels.cu", "fabe13_shim.cu"]
+HEADERS = ["fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libfabe13.so")
+
+
+def _stale():
+    if not os.path.exists(LIBPATH):
+        return True
+    t = os.path.getmtime(LIBPATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps += [os.path.join(HERE, "..", "include", f) for f in ("fabe13.h", "fabe13_cuda.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into lib/libfabe13.so.  Returns the path."""
+    if not force and not _stale():
+        return LIBPATH
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [
+        _nvcc(),
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-lineinfo", "-std=c++17",
+        "-shared", "-cudart", "static",
+        # host side: keep * and + as separate roundings (the host scalar API must match the device bit for bit)
+        "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-mfma,-fvisibility=hidden",
+        "-Xptxas", "-v" if verbose else "-O3",
+        "-o", LIBPATH,
+    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libfabe13.so")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIBPATH
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose="-v" in sys.argv))

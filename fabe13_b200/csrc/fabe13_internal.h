@@ -1,0 +1,42 @@
+// fabe13_internal.h -- interface between the C-ABI shim (fabe13_shim.cu) and the kernels (fabe13_kernels.cu).
+#ifndef FABE13_INTERNAL_H
+#define FABE13_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fabe13 {
+
+struct LaunchTuning {
+    int threads;        // threads per block of the streaming kernel (multiple of 32)
+    int blocks_per_sm;  // persistent grid = SMs * blocks_per_sm
+    int unroll;         // 256-bit vectors in flight per thread: 1, 2 or 4
+    int small_n;        // n below this runs the single inline kernel (no worklist, one launch)
+    int worklist_shift; // worklist capacity = n >> worklist_shift entries (0 = one entry per element)
+};
+
+struct DeviceInfo {
+    int device;
+    int sm_count;
+};
+
+// Bytes of scratch a launch over n elements needs for its Payne-Hanek worklist (header + entries).
+size_t workspace_bytes(size_t n, const LaunchTuning& t);
+
+// Enqueue the sincos path for n <= 2^31 elements on `stream`.  `workspace` must hold workspace_bytes(n) bytes
+// (it is zero-initialised here, on the stream).  d_k may be null.  Returns the number of kernels launched via
+// *launches.  Every pointer is a device pointer on the current device.
+cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int core,
+                          const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
+                          int* launches);
+
+// Bench/test hooks: synthetic inputs generated on the device (bit-identical to oracle/fabe13_oracle.c's fills).
+cudaError_t fill_uniform(double* d_out, size_t n, uint64_t seed, uint64_t first, double lo, double hi,
+                         const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t fill_loguniform(double* d_out, size_t n, uint64_t seed, uint64_t first, const DeviceInfo& dev,
+                            cudaStream_t stream);
+
+}  // namespace fabe13
+
+#endif  // FABE13_INTERNAL_H

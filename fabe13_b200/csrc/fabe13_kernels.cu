@@ -1,0 +1,405 @@
+// fabe13_kernels.cu -- sm_100a kernels for the FP64 array sincos path.
+//
+// Replaces the reference's SIMD array drivers fabe13_sincos_avx512 / _avx2 / _neon (fabe13/fabe13.c:545-614,
+// :469-541, :399-464) and their scalar tail loops (:339-358).  Three kernels:
+//
+//   sincos_stream_kernel   the hot path.  Persistent grid-stride loop; each thread streams 256-bit vectors
+//                          (LDG.E.NA.256 in, two STG.E.EF.256 out), UNROLL vectors in flight.  Per lane:
+//                          reference-exact k, Cody-Waite, polynomial/Psi core, integer-pipe fix-up.  24 B/element
+//                          of HBM traffic, no shared memory.  Lanes with |x| >= 2^45 are found with a warp
+//                          ballot, stash x in their sin slot and append their index to a compacted worklist.
+//   sincos_worklist_kernel second pass: one Payne-Hanek reduction per worklist entry, lanes densely packed.
+//   sincos_rescan_kernel   only does work if the worklist overflowed: rescans the sin array for stashed
+//                          arguments (a finite value >= 2^45 can never be a sine) and reduces them in place.
+//   sincos_inline_kernel   small n: one launch, every path inline.
+//
+// Data layout in HBM: three contiguous FP64 arrays (in, sin, cos), optional int64 k array (test hook), and a
+// workspace = { u32 count, pad to 32 B, u32 entries[cap] }.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fabe13_core.h"
+#include "fabe13_internal.h"
+
+namespace fabe13 {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWorklistHeaderBytes = 32;
+
+__constant__ uint64_t c_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
+
+struct StreamArgs {
+    const double* in;
+    double* sin_out;
+    double* cos_out;
+    long long* k_out;           // null unless WITH_K
+    uint32_t n;                 // elements in this launch (<= 2^31)
+    uint32_t head;              // scalar elements before the vector body
+    uint32_t nvec;              // vectors in the body
+    unsigned int* wl_count;     // worklist header
+    uint32_t* wl_entries;
+    uint32_t wl_cap;
+};
+
+// ---- 64/128/256-bit streaming accesses.  Loads do not allocate in L1 (each byte is read once); stores are
+//      evict-first.  Plain (coherent) loads, not .nc: in == sin_out is allowed.
+template <int VEC>
+__device__ __forceinline__ void load_stream(const double* p, uint64_t (&b)[VEC]);
+template <>
+__device__ __forceinline__ void load_stream<4>(const double* p, uint64_t (&b)[4]) {
+    asm volatile("ld.global.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(b[0]), "=l"(b[1]), "=l"(b[2]), "=l"(b[3])
+                 : "l"(p));
+}
+template <>
+__device__ __forceinline__ void load_stream<2>(const double* p, uint64_t (&b)[2]) {
+    asm volatile("ld.global.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(b[0]), "=l"(b[1]) : "l"(p));
+}
+template <>
+__device__ __forceinline__ void load_stream<1>(const double* p, uint64_t (&b)[1]) {
+    asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(b[0]) : "l"(p));
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_stream(void* p, const uint64_t (&b)[VEC]);
+template <>
+__device__ __forceinline__ void store_stream<4>(void* p, const uint64_t (&b)[4]) {
+    asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(b[0]), "l"(b[1]), "l"(b[2]), "l"(b[3])
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void store_stream<2>(void* p, const uint64_t (&b)[2]) {
+    asm volatile("st.global.cs.v2.b64 [%0], {%1,%2};" ::"l"(p), "l"(b[0]), "l"(b[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void store_stream<1>(void* p, const uint64_t (&b)[1]) {
+    asm volatile("st.global.cs.b64 [%0], %1;" ::"l"(p), "l"(b[0]) : "memory");
+}
+
+// ---- one lane of the fast path.  Returns true if the lane belongs to the Payne-Hanek pass; in that case the
+//      sin slot carries x itself (the second pass reads it back from there, so in-place calls stay correct).
+template <int CORE>
+__device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& cb, long long& k) {
+    const uint32_t ahi = (uint32_t)(xb >> 32) & 0x7FFFFFFFu;
+    const bool huge = (ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD);  // 2^45 <= |x| < Inf
+    const double x = __longlong_as_double((long long)xb);
+    int64_t kk;
+    const double kd = fabe13_quadrant_index(x, &kk);
+    const double r = fabe13_cody_waite(x, kd);
+    double sr, cr;
+    fabe13_core<CORE>(r, &sr, &cr);
+    fabe13_fixup(xb, sr, cr, (unsigned)kk & 3u, &sb, &cb);
+    sb = huge ? xb : sb;
+    k = (ahi >= 0x7FF00000u) ? 0 : kk;
+    return huge;
+}
+
+// Append the flagged lanes of this warp to the worklist (one atomic per warp per call).
+__device__ __forceinline__ void worklist_push(bool flag, uint32_t index, const StreamArgs& a, uint32_t lane) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(a.wl_count, (unsigned)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (flag) {
+        const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (slot < a.wl_cap) a.wl_entries[slot] = index;
+    }
+}
+
+template <int CORE, int VEC, int UNROLL, bool WITH_K>
+__global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t stride = gridDim.x * kThreads;
+    const double* in = a.in + a.head;
+    double* so = a.sin_out + a.head;
+    double* co = a.cos_out + a.head;
+
+    // warp-uniform trip count so that the ballots below always see a full warp
+    for (uint32_t wbase = gtid - lane; wbase < a.nvec; wbase += UNROLL * stride) {
+        uint64_t xb[UNROLL][VEC];
+        bool live[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t v = wbase + lane + u * stride;
+            live[u] = v < a.nvec;
+            if (live[u]) {
+                load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) xb[u][j] = 0;
+            }
+        }
+        bool any_huge = false;
+        uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
+        long long kk[UNROLL][VEC];
+        bool huge[UNROLL][VEC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                huge[u][j] = fast_lane<CORE>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+                any_huge |= huge[u][j];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (live[u]) {
+                const size_t e = (size_t)(wbase + lane + u * stride) * VEC;
+                store_stream<VEC>(so + e, sb[u]);
+                store_stream<VEC>(co + e, cb[u]);
+                if (WITH_K) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
+                }
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, any_huge)) {  // rare: compact the Payne-Hanek lanes
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const uint32_t idx = a.head + (wbase + lane + u * stride) * VEC + j;
+                    worklist_push(huge[u][j] && live[u], idx, a, lane);
+                }
+            }
+        }
+    }
+
+    // edges: the < VEC elements in front of the aligned body and the < VEC behind it (block 0, first warp)
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const uint32_t body_end = a.head + a.nvec * VEC;
+        const uint32_t n_edge = a.head + (a.n - body_end);
+        const bool on = lane < n_edge;
+        const uint32_t idx = lane < a.head ? lane : body_end + (lane - a.head);
+        uint64_t xb = 0, sb, cb;
+        long long k;
+        if (on) xb = (uint64_t)__double_as_longlong(a.in[idx]);
+        const bool huge = fast_lane<CORE>(xb, sb, cb, k) && on;
+        if (on) {
+            a.sin_out[idx] = __longlong_as_double((long long)sb);
+            a.cos_out[idx] = __longlong_as_double((long long)cb);
+            if (WITH_K) a.k_out[idx] = k;
+        }
+        worklist_push(huge, idx, a, lane);
+    }
+}
+
+struct SecondPassArgs {
+    double* sin_out;
+    double* cos_out;
+    long long* k_out;
+    uint32_t n;
+    const unsigned int* wl_count;
+    const uint32_t* wl_entries;
+    uint32_t wl_cap;
+};
+
+template <int CORE>
+__device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t idx, uint64_t xb, const uint64_t* table) {
+    uint64_t sb, cb;
+    int64_t k;
+    fabe13_sincos_one<CORE>(xb, table, &sb, &cb, &k);
+    a.sin_out[idx] = __longlong_as_double((long long)sb);
+    a.cos_out[idx] = __longlong_as_double((long long)cb);
+    if (a.k_out) a.k_out[idx] = k;
+}
+
+__device__ __forceinline__ void stage_table(uint64_t* table) {
+    if (threadIdx.x < FABE13_PH_WORDS) table[threadIdx.x] = c_ph_table[threadIdx.x];
+    __syncthreads();
+}
+
+// Second pass over the compacted worklist: every active lane runs Payne-Hanek.  The 2/pi table is staged in
+// shared memory because lanes index it by their own exponent (a divergent __constant__ read would serialise).
+template <int CORE>
+__global__ void __launch_bounds__(kThreads) sincos_worklist_kernel(const SecondPassArgs a) {
+    __shared__ uint64_t table[FABE13_PH_WORDS];
+    const uint32_t total = *a.wl_count;
+    if (total == 0) return;
+    stage_table(table);
+    const uint32_t cnt = total < a.wl_cap ? total : a.wl_cap;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) {
+        const uint32_t idx = a.wl_entries[i];
+        const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[idx]);
+        reduce_stashed<CORE>(a, idx, xb, table);
+    }
+}
+
+// Overflow pass: lanes that found the worklist full are still stashed in the sin array.
+template <int CORE>
+__global__ void __launch_bounds__(kThreads) sincos_rescan_kernel(const SecondPassArgs a) {
+    __shared__ uint64_t table[FABE13_PH_WORDS];
+    if (*a.wl_count <= a.wl_cap) return;
+    stage_table(table);
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < a.n; i += gridDim.x * kThreads) {
+        const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[i]);
+        const uint32_t ahi = (uint32_t)(xb >> 32) & 0x7FFFFFFFu;
+        if ((ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD)) reduce_stashed<CORE>(a, i, xb, table);
+    }
+}
+
+// Small n: launch latency is everything, so one kernel does every path inline.
+template <int CORE>
+__global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* in, double* sin_out, double* cos_out,
+                                                                  long long* k_out, uint32_t n) {
+    __shared__ uint64_t table[FABE13_PH_WORDS];
+    stage_table(table);
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const uint64_t xb = (uint64_t)__double_as_longlong(in[i]);
+        uint64_t sb, cb;
+        int64_t k;
+        fabe13_sincos_one<CORE>(xb, table, &sb, &cb, &k);
+        sin_out[i] = __longlong_as_double((long long)sb);
+        cos_out[i] = __longlong_as_double((long long)cb);
+        if (k_out) k_out[i] = k;
+    }
+}
+
+// ---- bench/test hooks: the synthetic inputs of SURVEY.md section 8d, generated in place on the device.
+//      Counter-based (splitmix64 of seed + global index), so any slice of any sharding reproduces the same array
+//      and the host generator in oracle/fabe13_oracle.c yields identical bits.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(kThreads) fill_uniform_kernel(double* out, size_t n, uint64_t seed, uint64_t first,
+                                                                 double lo, double hi) {
+    const double span = __dadd_rn(hi, -lo);
+    for (size_t i = blockIdx.x * (size_t)kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const double u = __dmul_rn(__ull2double_rn(splitmix64(seed + first + i) >> 11), 0x1.0p-53);
+        out[i] = __fma_rn(span, u, lo);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_loguniform_kernel(double* out, size_t n, uint64_t seed, uint64_t first) {
+    for (size_t i = blockIdx.x * (size_t)kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const uint64_t h = splitmix64(seed + first + i);
+        const uint64_t bits = ((h & 1u) << 63) | ((1023u + ((h >> 1) & 1023u)) << 52) | (splitmix64(h) >> 12);
+        out[i] = __longlong_as_double((long long)bits);
+    }
+}
+
+template <int CORE, int VEC, bool WITH_K>
+cudaError_t launch_stream_unroll(const StreamArgs& a, int unroll, int grid, cudaStream_t stream) {
+    switch (unroll) {
+        case 1: sincos_stream_kernel<CORE, VEC, 1, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
+        case 4: sincos_stream_kernel<CORE, VEC, 4, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
+        default: sincos_stream_kernel<CORE, VEC, 2, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+template <int CORE, bool WITH_K>
+cudaError_t launch_stream_vec(const StreamArgs& a, int vec, int unroll, int grid, cudaStream_t stream) {
+    switch (vec) {
+        case 4: return launch_stream_unroll<CORE, 4, WITH_K>(a, unroll, grid, stream);
+        case 2: return launch_stream_unroll<CORE, 2, WITH_K>(a, unroll, grid, stream);
+        default: return launch_stream_unroll<CORE, 1, WITH_K>(a, unroll, grid, stream);
+    }
+}
+
+template <int CORE>
+cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
+                        const LaunchTuning& t, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
+                        int* launches) {
+    if (n < (size_t)t.small_n || workspace == nullptr) {
+        const int need = (int)((n + kThreads - 1) / kThreads);
+        const int cap = dev.sm_count * 8;
+        sincos_inline_kernel<CORE><<<need < cap ? need : cap, kThreads, 0, stream>>>(d_in, d_sin, d_cos, d_k, (uint32_t)n);
+        *launches += 1;
+        return cudaGetLastError();
+    }
+
+    // widest vector all arrays can share: they must be congruent modulo the vector size
+    const uintptr_t pi = (uintptr_t)d_in, ps = (uintptr_t)d_sin, pc = (uintptr_t)d_cos;
+    int vec = 1;
+    for (int v = 4; v > 1; v >>= 1) {
+        const uintptr_t mask = (uintptr_t)v * 8 - 1;
+        if ((pi & mask) == (ps & mask) && (pi & mask) == (pc & mask)) {
+            vec = v;
+            break;
+        }
+    }
+    const uintptr_t vbytes = (uintptr_t)vec * 8;
+    uint32_t head = (uint32_t)(((vbytes - (pi & (vbytes - 1))) & (vbytes - 1)) / 8);
+    if (head > n) head = (uint32_t)n;
+
+    StreamArgs a;
+    a.in = d_in;
+    a.sin_out = d_sin;
+    a.cos_out = d_cos;
+    a.k_out = d_k;
+    a.n = (uint32_t)n;
+    a.head = head;
+    a.nvec = (uint32_t)((n - head) / vec);
+    a.wl_count = (unsigned int*)workspace;
+    a.wl_entries = (uint32_t*)((char*)workspace + kWorklistHeaderBytes);
+    a.wl_cap = (uint32_t)((workspace_bytes(n, t) - kWorklistHeaderBytes) / sizeof(uint32_t));
+
+    cudaError_t err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
+    if (err != cudaSuccess) return err;
+
+    const int unroll = (t.unroll == 1 || t.unroll == 4) ? t.unroll : 2;
+    const long long want = ((long long)a.nvec + (long long)kThreads * unroll - 1) / ((long long)kThreads * unroll);
+    const long long resident = (long long)dev.sm_count * t.blocks_per_sm;
+    int grid = (int)(want < resident ? want : resident);
+    if (grid < 1) grid = 1;
+    err = d_k ? launch_stream_vec<CORE, true>(a, vec, unroll, grid, stream)
+              : launch_stream_vec<CORE, false>(a, vec, unroll, grid, stream);
+    if (err != cudaSuccess) return err;
+
+    SecondPassArgs b;
+    b.sin_out = d_sin;
+    b.cos_out = d_cos;
+    b.k_out = d_k;
+    b.n = (uint32_t)n;
+    b.wl_count = a.wl_count;
+    b.wl_entries = a.wl_entries;
+    b.wl_cap = a.wl_cap;
+    const int grid2 = dev.sm_count * 4;
+    sincos_worklist_kernel<CORE><<<grid2, kThreads, 0, stream>>>(b);
+    sincos_rescan_kernel<CORE><<<grid2, kThreads, 0, stream>>>(b);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t workspace_bytes(size_t n, const LaunchTuning& t) {
+    size_t cap = n >> t.worklist_shift;
+    if (cap < 1024) cap = 1024;
+    return (size_t)kWorklistHeaderBytes + cap * sizeof(uint32_t);
+}
+
+cudaError_t fill_uniform(double* d_out, size_t n, uint64_t seed, uint64_t first, double lo, double hi,
+                         const DeviceInfo& dev, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fill_uniform_kernel<<<dev.sm_count * 8, kThreads, 0, stream>>>(d_out, n, seed, first, lo, hi);
+    return cudaGetLastError();
+}
+
+cudaError_t fill_loguniform(double* d_out, size_t n, uint64_t seed, uint64_t first, const DeviceInfo& dev,
+                            cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fill_loguniform_kernel<<<dev.sm_count * 8, kThreads, 0, stream>>>(d_out, n, seed, first);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int core,
+                          const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
+                          int* launches) {
+    if (n == 0) return cudaSuccess;
+    if (n > ((size_t)1 << 31)) return cudaErrorInvalidValue;
+    if (core == FABE13_CORE_PSI)
+        return launch_core<FABE13_CORE_PSI>(d_in, d_sin, d_cos, d_k, n, tuning, dev, workspace, stream, launches);
+    return launch_core<FABE13_CORE_POLY>(d_in, d_sin, d_cos, d_k, n, tuning, dev, workspace, stream, launches);
+}
+
+}  // namespace fabe13

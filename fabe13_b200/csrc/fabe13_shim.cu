@@ -1,0 +1,614 @@
+// fabe13_shim.cu -- the C ABI of libfabe13.so: the reference's fabe13.h entry points plus the CUDA extension
+// (include/fabe13_cuda.h), over the CUDA runtime.
+//
+// Mirrors the reference's dispatcher layer (fabe13/fabe13.c:132-135 global state, :186-219 initialisation and
+// getters, :222-259 fabe13_sincos, :262-269 scalar API) with the ISA switch replaced by: device pointers -> one
+// stream-ordered launch sequence; host pointers -> chunked H2D | kernel | D2H pipeline.  There is no CPU fallback
+// for the array path: a CUDA failure is recorded, reported on stderr and returned.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#pragma GCC visibility push(default)  // the library is built with -fvisibility=hidden; only the C ABI is exported
+#include "../../include/fabe13.h"
+#include "../../include/fabe13_cuda.h"
+#pragma GCC visibility pop
+#include "fabe13_core.h"
+#include "fabe13_internal.h"
+
+namespace {
+
+using fabe13::DeviceInfo;
+using fabe13::LaunchTuning;
+
+constexpr int kMaxDevices = 64;
+constexpr int kSlots = 4;                                  // pipeline depth of the host path
+constexpr size_t kLaunchMaxElems = (size_t)1 << 30;        // per launch sequence; keeps 32-bit indices and alignment
+
+const uint64_t h_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
+
+// ---------------------------------------------------------------------------------------------------------------
+// configuration (reference: compile-time constants fabe13/fabe13.c:71-73; here run-time options)
+// ---------------------------------------------------------------------------------------------------------------
+struct Config {
+    std::atomic<long long> core{FABE13_CORE_POLY};
+    std::atomic<long long> blocks_per_sm{4};
+    std::atomic<long long> unroll{2};
+    std::atomic<long long> small_n{16384};
+    std::atomic<long long> worklist_shift{3};
+    std::atomic<long long> chunk_elems{(long long)1 << 22};
+    std::atomic<long long> host_devices{1};
+    std::atomic<long long> stage_threads{4};
+};
+
+Config g_cfg;
+std::once_flag g_cfg_once;
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_last_error{0};
+
+struct OptionDesc {
+    const char* key;
+    const char* env;
+    std::atomic<long long> Config::*field;
+    long long lo, hi;
+};
+
+const OptionDesc kOptions[] = {
+    {"core", "FABE13_CUDA_CORE", &Config::core, 0, 1},
+    {"blocks_per_sm", "FABE13_CUDA_BLOCKS_PER_SM", &Config::blocks_per_sm, 1, 32},
+    {"unroll", "FABE13_CUDA_UNROLL", &Config::unroll, 1, 4},
+    {"small_n", "FABE13_CUDA_SMALL_N", &Config::small_n, 0, (long long)1 << 30},
+    {"worklist_shift", "FABE13_CUDA_WORKLIST_SHIFT", &Config::worklist_shift, 0, 20},
+    {"chunk_elems", "FABE13_CUDA_CHUNK_ELEMS", &Config::chunk_elems, 1024, (long long)1 << 28},
+    {"host_devices", "FABE13_CUDA_HOST_DEVICES", &Config::host_devices, 1, kMaxDevices},
+    {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 1, kSlots},
+};
+
+void load_env() {
+    std::call_once(g_cfg_once, [] {
+        for (const OptionDesc& o : kOptions) {
+            const char* v = getenv(o.env);
+            if (!v || !*v) continue;
+            long long x;
+            if (strcmp(o.key, "core") == 0 && (strcmp(v, "psi") == 0 || strcmp(v, "poly") == 0 || strcmp(v, "estrin") == 0))
+                x = strcmp(v, "psi") == 0 ? 1 : 0;
+            else
+                x = atoll(v);
+            if (x >= o.lo && x <= o.hi) (g_cfg.*(o.field)).store(x);
+        }
+    });
+}
+
+LaunchTuning current_tuning() {
+    load_env();
+    LaunchTuning t;
+    t.threads = 256;
+    t.blocks_per_sm = (int)g_cfg.blocks_per_sm.load();
+    t.unroll = (int)g_cfg.unroll.load();
+    t.small_n = (int)g_cfg.small_n.load();
+    t.worklist_shift = (int)g_cfg.worklist_shift.load();
+    return t;
+}
+
+int record(cudaError_t e, const char* where) {
+    if (e == cudaSuccess) return 0;
+    g_last_error.store((int)e);
+    fprintf(stderr, "fabe13: CUDA error %d (%s) in %s\n", (int)e, cudaGetErrorString(e), where);
+    const char* ab = getenv("FABE13_CUDA_ABORT");
+    if (ab && *ab == '1') abort();
+    (void)cudaGetLastError();  // clear the non-sticky error state so later calls are not poisoned
+    return (int)e;
+}
+
+#define FABE13_TRY(expr)                               \
+    do {                                               \
+        cudaError_t e__ = (expr);                      \
+        if (e__ != cudaSuccess) return record(e__, #expr); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-device state, created on first use (reference: load-time constructor fabe13/fabe13.c:209-214)
+// ---------------------------------------------------------------------------------------------------------------
+struct Slot {
+    cudaStream_t stream = nullptr;
+    double* d_in = nullptr;   // chunk_cap elements each
+    double* d_sin = nullptr;
+    double* d_cos = nullptr;
+    void* d_ws = nullptr;
+    double* h_in = nullptr;   // pinned staging, allocated only when a pageable buffer shows up
+    double* h_sin = nullptr;
+    double* h_cos = nullptr;
+};
+
+struct DeviceState {
+    std::mutex init_mu;
+    bool ready = false;
+    DeviceInfo info{};
+    cudaMemPool_t pool = nullptr;  // stream-ordered scratch for the device-pointer entry points
+    char name[256] = {0};
+    // host path
+    std::mutex pipe_mu;
+    size_t chunk_cap = 0;
+    size_t ws_bytes = 0;
+    bool staging = false;
+    Slot slots[kSlots];
+};
+
+DeviceState g_dev[kMaxDevices];
+
+int device_state(int dev, DeviceState** out) {
+    if (dev < 0 || dev >= kMaxDevices) return record(cudaErrorInvalidDevice, "device_state");
+    DeviceState& s = g_dev[dev];
+    std::lock_guard<std::mutex> lk(s.init_mu);
+    if (!s.ready) {
+        cudaDeviceProp prop;
+        FABE13_TRY(cudaGetDeviceProperties(&prop, dev));
+        s.info.device = dev;
+        s.info.sm_count = prop.multiProcessorCount;
+        snprintf(s.name, sizeof s.name, "CUDA sm_%d%d (%s, %d SMs)", prop.major, prop.minor, prop.name,
+                 prop.multiProcessorCount);
+        cudaMemPoolProps pp;
+        memset(&pp, 0, sizeof pp);
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = dev;
+        FABE13_TRY(cudaMemPoolCreate(&s.pool, &pp));
+        unsigned long long keep = ~0ull;  // never trim: the worklist scratch is reused call after call
+        FABE13_TRY(cudaMemPoolSetAttribute(s.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        s.ready = true;
+    }
+    *out = &s;
+    return 0;
+}
+
+int current_device_state(DeviceState** out) {
+    int dev = 0;
+    FABE13_TRY(cudaGetDevice(&dev));
+    return device_state(dev, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-pointer path
+// ---------------------------------------------------------------------------------------------------------------
+int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, void* user_ws,
+               size_t user_ws_bytes, cudaStream_t stream) {
+    if (n == 0) return 0;
+    DeviceState* ds;
+    if (int rc = current_device_state(&ds)) return rc;
+    const LaunchTuning t = current_tuning();
+    const int core = (int)g_cfg.core.load();
+    for (size_t off = 0; off < n; off += kLaunchMaxElems) {
+        const size_t m = (n - off < kLaunchMaxElems) ? n - off : kLaunchMaxElems;
+        void* ws = nullptr;
+        bool pooled = false;
+        if (m >= (size_t)t.small_n) {
+            const size_t need = fabe13::workspace_bytes(m, t);
+            if (user_ws) {
+                if (user_ws_bytes < need) return record(cudaErrorInvalidValue, "workspace too small");
+                ws = user_ws;
+            } else {
+                FABE13_TRY(cudaMallocFromPoolAsync(&ws, need, ds->pool, stream));
+                pooled = true;
+            }
+        }
+        int launches = 0;
+        cudaError_t e = fabe13::launch_sincos(d_in + off, d_sin + off, d_cos + off, d_k ? d_k + off : nullptr, m, core,
+                                              t, ds->info, ws, stream, &launches);
+        g_launches.fetch_add((unsigned long long)launches);
+        if (pooled) {
+            cudaError_t e2 = cudaFreeAsync(ws, stream);
+            if (e == cudaSuccess) e = e2;
+        }
+        if (e != cudaSuccess) return record(e, "launch_sincos");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-pointer path: chunked pipeline through per-device slots
+// ---------------------------------------------------------------------------------------------------------------
+enum PtrKind { PTR_PAGEABLE, PTR_PINNED, PTR_DEVICE };
+
+PtrKind classify(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return PTR_PAGEABLE;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return PTR_DEVICE;
+    if (a.type == cudaMemoryTypeHost) return PTR_PINNED;
+    return PTR_PAGEABLE;
+}
+
+void free_slots(DeviceState& s) {
+    for (Slot& sl : s.slots) {
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.d_sin) cudaFree(sl.d_sin);
+        if (sl.d_cos) cudaFree(sl.d_cos);
+        if (sl.d_ws) cudaFree(sl.d_ws);
+        if (sl.h_in) cudaFreeHost(sl.h_in);
+        if (sl.h_sin) cudaFreeHost(sl.h_sin);
+        if (sl.h_cos) cudaFreeHost(sl.h_cos);
+        sl.d_in = sl.d_sin = sl.d_cos = nullptr;
+        sl.d_ws = nullptr;
+        sl.h_in = sl.h_sin = sl.h_cos = nullptr;
+    }
+    s.chunk_cap = 0;
+    s.staging = false;
+}
+
+// (re)size the slots of the current device for `chunk` elements; pinned staging only if asked for
+int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning& t) {
+    if (s.chunk_cap < chunk) {
+        free_slots(s);
+        s.ws_bytes = fabe13::workspace_bytes(chunk, t);
+        for (Slot& sl : s.slots) {
+            if (!sl.stream) FABE13_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            FABE13_TRY(cudaMalloc(&sl.d_in, chunk * sizeof(double)));
+            FABE13_TRY(cudaMalloc(&sl.d_sin, chunk * sizeof(double)));
+            FABE13_TRY(cudaMalloc(&sl.d_cos, chunk * sizeof(double)));
+            FABE13_TRY(cudaMalloc(&sl.d_ws, s.ws_bytes));
+        }
+        s.chunk_cap = chunk;
+    }
+    if (staging && !s.staging) {
+        for (Slot& sl : s.slots) {
+            FABE13_TRY(cudaHostAlloc(&sl.h_in, s.chunk_cap * sizeof(double), cudaHostAllocDefault));
+            FABE13_TRY(cudaHostAlloc(&sl.h_sin, s.chunk_cap * sizeof(double), cudaHostAllocDefault));
+            FABE13_TRY(cudaHostAlloc(&sl.h_cos, s.chunk_cap * sizeof(double), cudaHostAllocDefault));
+        }
+        s.staging = true;
+    }
+    return 0;
+}
+
+size_t pick_chunk(size_t n) {
+    const size_t cap = (size_t)g_cfg.chunk_elems.load();
+    size_t c = (n + 5) / 6;  // at least ~6 chunks so the three stages overlap
+    if (c < 131072) c = 131072;
+    if (c > cap) c = cap;
+    if (c > n) c = n;
+    return (c + 3) & ~(size_t)3;
+}
+
+// enqueue one chunk on a slot: H2D, kernels, 2x D2H.  src/dst are pinned (user memory or staging).
+int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, double* dst_cos, size_t m,
+                  const LaunchTuning& t, int core) {
+    FABE13_TRY(cudaMemcpyAsync(sl.d_in, src, m * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
+    int launches = 0;
+    cudaError_t e = fabe13::launch_sincos(sl.d_in, sl.d_sin, sl.d_cos, nullptr, m, core, t, s.info,
+                                          m >= (size_t)t.small_n ? sl.d_ws : nullptr, sl.stream, &launches);
+    g_launches.fetch_add((unsigned long long)launches);
+    if (e != cudaSuccess) return record(e, "launch_sincos(host path)");
+    FABE13_TRY(cudaMemcpyAsync(dst_sin, sl.d_sin, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    FABE13_TRY(cudaMemcpyAsync(dst_cos, sl.d_cos, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    return 0;
+}
+
+// One device, one contiguous slice.  Caller has made `dev` current.
+int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned) {
+    DeviceState* ds;
+    if (int rc = device_state(dev, &ds)) return rc;
+    std::lock_guard<std::mutex> lk(ds->pipe_mu);
+    const LaunchTuning t = current_tuning();
+    const int core = (int)g_cfg.core.load();
+    const size_t chunk = pick_chunk(n);
+    if (int rc = ensure_slots(*ds, chunk, !pinned, t)) return rc;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+
+    if (pinned) {
+        // copy engines read and write the caller's pinned memory directly; one host thread feeds all slots
+        for (size_t i = 0; i < nchunks; ++i) {
+            const size_t off = i * chunk;
+            const size_t m = n - off < chunk ? n - off : chunk;
+            if (int rc = enqueue_chunk(*ds, ds->slots[i % kSlots], in + off, sin_out + off, cos_out + off, m, t, core))
+                return rc;
+        }
+        for (Slot& sl : ds->slots) FABE13_TRY(cudaStreamSynchronize(sl.stream));
+        return 0;
+    }
+
+    // pageable memory: worker w owns slot w and the chunks i = w (mod workers); it copies the chunk into pinned
+    // staging, runs it, waits, and copies the results out.  Workers overlap each other's stages.
+    int workers = (int)g_cfg.stage_threads.load();
+    if ((size_t)workers > nchunks) workers = (int)nchunks;
+    std::atomic<int> rc_all{0};
+    auto work = [&](int w) {
+        if (cudaSetDevice(dev) != cudaSuccess) {
+            rc_all.store(record(cudaErrorInvalidDevice, "cudaSetDevice(worker)"));
+            return;
+        }
+        Slot& sl = ds->slots[w];
+        for (size_t i = (size_t)w; i < nchunks && rc_all.load() == 0; i += (size_t)workers) {
+            const size_t off = i * chunk;
+            const size_t m = n - off < chunk ? n - off : chunk;
+            memcpy(sl.h_in, in + off, m * sizeof(double));
+            int rc = enqueue_chunk(*ds, sl, sl.h_in, sl.h_sin, sl.h_cos, m, t, core);
+            if (rc == 0) {
+                cudaError_t e = cudaStreamSynchronize(sl.stream);
+                if (e != cudaSuccess) rc = record(e, "cudaStreamSynchronize(worker)");
+            }
+            if (rc != 0) {
+                rc_all.store(rc);
+                return;
+            }
+            memcpy(sin_out + off, sl.h_sin, m * sizeof(double));
+            memcpy(cos_out + off, sl.h_cos, m * sizeof(double));
+        }
+    };
+    if (workers <= 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
+        work(0);
+        for (std::thread& x : th) x.join();
+    }
+    return rc_all.load();
+}
+
+int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
+    if (n == 0) return 0;
+    load_env();
+    const PtrKind ki = classify(in), ks = classify(sin_out), kc = classify(cos_out);
+    if (ki == PTR_DEVICE || ks == PTR_DEVICE || kc == PTR_DEVICE) {
+        if (!(ki == PTR_DEVICE && ks == PTR_DEVICE && kc == PTR_DEVICE))
+            return record(cudaErrorInvalidValue, "fabe13_sincos: mixed host and device pointers");
+        if (int rc = run_device(in, sin_out, cos_out, nullptr, n, nullptr, 0, nullptr)) return rc;
+        FABE13_TRY(cudaStreamSynchronize(nullptr));
+        return 0;
+    }
+    const bool pinned = (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED);
+    int cur = 0;
+    FABE13_TRY(cudaGetDevice(&cur));
+    int ndev_avail = 0;
+    FABE13_TRY(cudaGetDeviceCount(&ndev_avail));
+    int ndev = (int)g_cfg.host_devices.load();
+    if (ndev > ndev_avail) ndev = ndev_avail;
+    if (ndev <= 1 || n < ((size_t)1 << 20)) return host_slice(cur, in, sin_out, cos_out, n, pinned);
+
+    // contiguous slice per GPU, one host thread each; no exchange between slices
+    std::vector<std::thread> th;
+    std::vector<int> rcs((size_t)ndev, 0);
+    for (int g = 0; g < ndev; ++g) {
+        th.emplace_back([&, g] {
+            size_t b, e;
+            fabe13_shard_bounds(n, ndev, g, &b, &e);
+            const int dev = (cur + g) % ndev_avail;
+            if (cudaSetDevice(dev) != cudaSuccess) {
+                rcs[(size_t)g] = record(cudaErrorInvalidDevice, "cudaSetDevice(slice)");
+                return;
+            }
+            if (e > b) rcs[(size_t)g] = host_slice(dev, in + b, sin_out + b, cos_out + b, e - b, pinned);
+        });
+    }
+    for (std::thread& x : th) x.join();
+    for (int rc : rcs)
+        if (rc) return rc;
+    return 0;
+}
+
+int cfg_core() {
+    load_env();
+    return (int)g_cfg.core.load();
+}
+
+void host_one(double x, int core, double* s, double* c, long long* k) {
+    uint64_t sb, cb;
+    int64_t kk;
+    if (core == FABE13_CORE_PSI)
+        fabe13_sincos_one<FABE13_CORE_PSI>(fabe13_bits(x), h_ph_table, &sb, &cb, &kk);
+    else
+        fabe13_sincos_one<FABE13_CORE_POLY>(fabe13_bits(x), h_ph_table, &sb, &cb, &kk);
+    *s = fabe13_from_bits(sb);
+    *c = fabe13_from_bits(cb);
+    if (k) *k = (long long)kk;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void fabe13_sincos(const double* in, double* sin_out, double* cos_out, int n) {
+    if (n <= 0) return;  // reference fabe13/fabe13.c:223
+    (void)run_host(in, sin_out, cos_out, (size_t)n);
+}
+
+int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n) {
+    return run_host(in, sin_out, cos_out, n);
+}
+
+const char* fabe13_get_active_implementation_name(void) {
+    DeviceState* ds;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return "CUDA sm_100a (no device visible)";
+    }
+    if (current_device_state(&ds) != 0) return "CUDA sm_100a (device initialisation failed)";
+    return ds->name;
+}
+
+int fabe13_get_active_simd_width(void) { return 32; }
+
+// scalar API: host instantiation of the array core (reference fabe13/fabe13.c:262-269)
+double fabe13_sin(double x) {
+    double s, c;
+    host_one(x, cfg_core(), &s, &c, nullptr);
+    return s;
+}
+double fabe13_cos(double x) {
+    double s, c;
+    host_one(x, cfg_core(), &s, &c, nullptr);
+    return c;
+}
+double fabe13_sinc(double x) {
+    if (fabs(x) < 1e-9) return 1.0;
+    double s, c;
+    host_one(x, cfg_core(), &s, &c, nullptr);
+    return s / x;
+}
+double fabe13_tan(double x) {
+    double s, c;
+    host_one(x, cfg_core(), &s, &c, nullptr);
+    if (c == 0.0) return NAN;
+    return s / c;
+}
+double fabe13_cot(double x) {
+    double s, c;
+    host_one(x, cfg_core(), &s, &c, nullptr);
+    if (s == 0.0) return NAN;
+    return c / s;
+}
+double fabe13_atan(double x) { return atan(x); }
+double fabe13_asin(double x) { return asin(x); }
+double fabe13_acos(double x) { return acos(x); }
+
+int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream) {
+    return run_device(d_in, d_sin, d_cos, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+}
+
+int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
+                           void* cuda_stream) {
+    return run_device(d_in, d_sin, d_cos, d_k, n, nullptr, 0, (cudaStream_t)cuda_stream);
+}
+
+size_t fabe13_sincos_workspace_bytes(size_t n) {
+    const LaunchTuning t = current_tuning();
+    return fabe13::workspace_bytes(n < kLaunchMaxElems ? n : kLaunchMaxElems, t);
+}
+
+int fabe13_sincos_device_ws(const double* d_in, double* d_sin, double* d_cos, size_t n, void* workspace,
+                            size_t workspace_bytes, void* cuda_stream) {
+    if (!workspace) return record(cudaErrorInvalidValue, "fabe13_sincos_device_ws: null workspace");
+    return run_device(d_in, d_sin, d_cos, nullptr, n, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in, double* const* d_sin,
+                        double* const* d_cos, const size_t* n_per_dev) {
+    int cur = 0;
+    FABE13_TRY(cudaGetDevice(&cur));
+    int rc = 0;
+    for (int g = 0; g < ngpu && rc == 0; ++g) {
+        cudaError_t e = cudaSetDevice(devices[g]);
+        if (e != cudaSuccess) {
+            rc = record(e, "cudaSetDevice(multi)");
+            break;
+        }
+        rc = run_device(d_in[g], d_sin[g], d_cos[g], nullptr, n_per_dev[g], nullptr, 0, nullptr);
+    }
+    for (int g = 0; g < ngpu; ++g) {
+        if (cudaSetDevice(devices[g]) != cudaSuccess) continue;
+        cudaError_t e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess && rc == 0) rc = record(e, "cudaStreamSynchronize(multi)");
+    }
+    (void)cudaSetDevice(cur);
+    return rc;
+}
+
+void* fabe13_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        record(cudaErrorMemoryAllocation, "fabe13_cuda_host_alloc");
+        return nullptr;
+    }
+    return p;
+}
+
+void fabe13_cuda_host_free(void* p) {
+    if (p) (void)cudaFreeHost(p);
+}
+
+void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end) {
+    if (world < 1) world = 1;
+    if (rank < 0) rank = 0;
+    if (rank >= world) rank = world - 1;
+    const size_t per = (n / (size_t)world) & ~(size_t)3;
+    *begin = per * (size_t)rank;
+    *end = (rank == world - 1) ? n : per * (size_t)(rank + 1);
+}
+
+int fabe13_cuda_set_option(const char* key, long long value) {
+    load_env();
+    for (const OptionDesc& o : kOptions) {
+        if (strcmp(o.key, key) == 0) {
+            if (value < o.lo || value > o.hi) return -2;
+            (g_cfg.*(o.field)).store(value);
+            return 0;
+        }
+    }
+    return -1;
+}
+
+int fabe13_cuda_get_option(const char* key, long long* value) {
+    load_env();
+    for (const OptionDesc& o : kOptions) {
+        if (strcmp(o.key, key) == 0) {
+            *value = (g_cfg.*(o.field)).load();
+            return 0;
+        }
+    }
+    if (strcmp(key, "launches") == 0) {
+        *value = (long long)g_launches.load();
+        return 0;
+    }
+    if (strcmp(key, "device_count") == 0) {
+        *value = fabe13_cuda_device_count();
+        return 0;
+    }
+    if (strcmp(key, "sm_count") == 0) {
+        DeviceState* ds;
+        if (int rc = current_device_state(&ds)) return rc;
+        *value = ds->info.sm_count;
+        return 0;
+    }
+    return -1;
+}
+
+int fabe13_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fabe13_cuda_last_error(void) { return g_last_error.load(); }
+
+const char* fabe13_cuda_last_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_error.load()); }
+
+void fabe13_cuda_clear_error(void) { g_last_error.store(0); }
+
+void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core) {
+    for (size_t i = 0; i < n; ++i) host_one(in[i], core, &sin_out[i], &cos_out[i], k_out ? &k_out[i] : nullptr);
+}
+
+int fabe13_debug_fill_uniform_device(double* d_out, size_t n, unsigned long long seed, unsigned long long first_index,
+                                     double lo, double hi, void* cuda_stream) {
+    DeviceState* ds;
+    if (int rc = current_device_state(&ds)) return rc;
+    FABE13_TRY(fabe13::fill_uniform(d_out, n, seed, first_index, lo, hi, ds->info, (cudaStream_t)cuda_stream));
+    return 0;
+}
+
+int fabe13_debug_fill_loguniform_device(double* d_out, size_t n, unsigned long long seed,
+                                        unsigned long long first_index, void* cuda_stream) {
+    DeviceState* ds;
+    if (int rc = current_device_state(&ds)) return rc;
+    FABE13_TRY(fabe13::fill_loguniform(d_out, n, seed, first_index, ds->info, (cudaStream_t)cuda_stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+/*
+ * fabe13_cuda.h -- additive CUDA entry points of libfabe13.so (B200 / sm_100a).
+ *
+ * The reference has no device API; these are the functions a binding for the array path would call when the data
+ * already lives in GPU memory.  Each one replaces a call to the reference's fabe13_sincos (fabe13/fabe13.h:51-56,
+ * implementation fabe13/fabe13.c:222-259) for device-resident arrays.  Plain C ABI: pointers, sizes, an opaque
+ * stream handle (a cudaStream_t passed as void*).  All functions returning int return 0 on success or a
+ * cudaError_t value; the last non-zero value is also kept for fabe13_cuda_last_error().
+ */
+#ifndef FABE13_CUDA_H
+#define FABE13_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-element core selection (option "core"). */
+#define FABE13_CUDA_CORE_POLY 0 /* direct minimax kernels: 24 FP64 instructions per element (default) */
+#define FABE13_CUDA_CORE_PSI 1  /* Psi-Hyperbasis rational core + correction polynomials */
+
+/* Asynchronous sincos over n device-resident doubles on `cuda_stream` (NULL = legacy default stream).
+ * d_in, d_sin, d_cos are device pointers on the current device, 8-byte aligned; d_in == d_sin is allowed.
+ * Scratch for the Payne-Hanek worklist is taken from a library-owned stream-ordered memory pool. */
+int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream);
+
+/* Same, and also writes the quadrant index per element (test hook for the k-parity contract):
+ * d_k[i] = rint(x*2/pi) by the reference's sequence for |x| < 2^45; k mod 4 (0..3) for 2^45 <= |x| < Inf;
+ * 0 for NaN/Inf. */
+int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
+                           void* cuda_stream);
+
+/* Same as fabe13_sincos_device with caller-provided scratch of at least fabe13_sincos_workspace_bytes(n) bytes
+ * (no allocation on the call path; usable inside CUDA graph capture on any toolkit). */
+size_t fabe13_sincos_workspace_bytes(size_t n);
+int fabe13_sincos_device_ws(const double* d_in, double* d_sin, double* d_cos, size_t n, void* workspace,
+                            size_t workspace_bytes, void* cuda_stream);
+
+/* One slice per GPU, no exchange between them: launches on every listed device, then waits for all.
+ * d_in[g], d_sin[g], d_cos[g] live on devices[g] and hold n_per_dev[g] elements. */
+int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in, double* const* d_sin,
+                        double* const* d_cos, const size_t* n_per_dev);
+
+/* Host-pointer entry with a size_t length and an error return; fabe13_sincos() forwards here.
+ * Pinned host memory (cudaHostAlloc / cudaHostRegister / fabe13_cuda_host_alloc) is copied directly by the copy
+ * engines, H2D and D2H overlapped with the kernel chunk by chunk; pageable memory goes through pinned staging
+ * buffers filled by worker threads.  With option "host_devices" > 1 the array is split into contiguous slices,
+ * one per GPU. */
+int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n);
+
+/* Pinned host allocations for the fast host path. */
+void* fabe13_cuda_host_alloc(size_t bytes);
+void fabe13_cuda_host_free(void* p);
+
+/* Contiguous slice [begin, end) of an n-element array owned by `rank` of `world` ranks; interior boundaries are
+ * multiples of 4 elements so every slice keeps 32-byte alignment.  The remainder goes to the last rank. */
+void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
+
+/* Options: "core" (0/1), "blocks_per_sm", "unroll" (1/2/4), "small_n", "worklist_shift", "chunk_elems",
+ * "host_devices", "stage_threads".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
+ * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
+int fabe13_cuda_set_option(const char* key, long long value);
+int fabe13_cuda_get_option(const char* key, long long* value);
+
+int fabe13_cuda_device_count(void);
+int fabe13_cuda_last_error(void);               /* last non-zero cudaError_t seen by this library, 0 if none */
+const char* fabe13_cuda_last_error_string(void);
+void fabe13_cuda_clear_error(void);
+
+/* Test hook, never on a product path: evaluates the shared per-element core on the HOST for n elements
+ * (same code the kernels compile for the device).  Lets CPU-only CI check the algorithm without a GPU. */
+void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core);
+
+/* Bench/test hooks: fill a device array with the deterministic synthetic inputs used by bench.py and the parity
+ * tests (counter-based splitmix64; the same generator exists on the host in oracle/fabe13_oracle.c).
+ * uniform: x_i = fma(hi-lo, u_i, lo), u_i in [0,1);  loguniform: |x| log-uniform over [1, 2^1024), random sign. */
+int fabe13_debug_fill_uniform_device(double* d_out, size_t n, unsigned long long seed, unsigned long long first_index,
+                                     double lo, double hi, void* cuda_stream);
+int fabe13_debug_fill_loguniform_device(double* d_out, size_t n, unsigned long long seed,
+                                        unsigned long long first_index, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FABE13_CUDA_H */

@@ -1,0 +1,123 @@
+"""The drop-in boundary: libfabe13.so loads without a GPU and exports every function include/*.h declares, with the
+reference's names and signatures; host-side logic (options, slice bounds, scalar API) behaves as documented.
+No GPU compute is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# the reference's public API: fabe13/fabe13.h:51-56, :62, :68, :71-78
+REFERENCE_API = ["fabe13_sincos", "fabe13_get_active_implementation_name", "fabe13_get_active_simd_width", "fabe13_sin",
+                 "fabe13_cos", "fabe13_sinc", "fabe13_tan", "fabe13_cot", "fabe13_atan", "fabe13_asin", "fabe13_acos"]
+
+
+def declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    return sorted(set(re.findall(r"\b(fabe13_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(fabe13):
+    from fabe13_b200 import _lib
+
+    lib = _lib.load()
+    names = declared_functions("fabe13.h") + declared_functions("fabe13_cuda.h")
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported by libfabe13.so"
+    # and the Python binding declares a signature for each of them
+    assert set(names) == set(_lib.signatures())
+
+
+def test_reference_api_is_complete(fabe13):
+    assert set(REFERENCE_API) <= set(declared_functions("fabe13.h"))
+    hdr = open(os.path.join(ROOT, "include", "fabe13.h")).read()
+    assert re.search(r"#define\s+FABE13_ALIGNMENT\s+64", hdr)
+    assert 'extern "C"' in hdr
+
+
+def test_reference_programs_compile_against_our_header(tmp_path):
+    """A C program written against the reference API compiles and links against include/fabe13.h + libfabe13.so."""
+    src = tmp_path / "user.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "fabe13.h"\n'
+        "int main(void){double in[4]={0.5,1,2,3},s[4],c[4];\n"
+        ' printf("%s %d %d\\n", fabe13_get_active_implementation_name(), fabe13_get_active_simd_width(), FABE13_ALIGNMENT);\n'
+        ' printf("%.17g %.17g %.17g\\n", fabe13_sin(1.0), fabe13_cos(1.0), fabe13_tan(0.5));\n'
+        " (void)in;(void)s;(void)c; return 0;}\n"
+    )
+    exe = tmp_path / "user"
+    libdir = os.path.join(ROOT, "fabe13_b200", "lib")
+    import subprocess
+
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lfabe13", f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0].startswith("CUDA sm_100a") and out[0].rstrip().endswith("32 64")
+    s, c, t = (float(v) for v in out[1].split())
+    assert abs(s - np.sin(1.0)) < 2e-16 and abs(c - np.cos(1.0)) < 2e-16 and abs(t - np.tan(0.5)) < 4e-16
+
+
+def test_getters_without_gpu(fabe13):
+    assert fabe13.simd_width() == 32
+    assert fabe13.implementation_name().startswith("CUDA sm_100a")
+
+
+def test_shard_bounds_cover_and_align(fabe13):
+    for n in (0, 1, 7, 10, 1000, 10**6 + 3, 10**9, 2**31 + 5):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for rank in range(world):
+                b, e = fabe13.shard_bounds(n, world, rank)
+                assert b == prev and e >= b
+                if rank < world - 1:
+                    assert e % 4 == 0  # interior cuts keep 32-byte alignment
+                prev = e
+            assert prev == n
+    b, e = fabe13.shard_bounds(10**9, 8, 3)
+    assert (b, e) == (375000000, 500000000)
+
+
+def test_options_roundtrip_and_validation(fabe13):
+    old = fabe13.get_option("unroll")
+    fabe13.set_option("unroll", 4)
+    assert fabe13.get_option("unroll") == 4
+    fabe13.set_option("unroll", old)
+    with pytest.raises(ValueError):
+        fabe13.set_option("unroll", 99)
+    with pytest.raises(ValueError):
+        fabe13.set_option("no_such_option", 1)
+    with pytest.raises(KeyError):
+        fabe13.get_option("no_such_option")
+    assert fabe13.get_option("launches") >= 0
+    ws = fabe13._lib.load().fabe13_sincos_workspace_bytes(10**8) if hasattr(fabe13, "_lib") else None
+    assert ws is None or ws >= 32 + 4 * (10**8 >> 3)
+
+
+def test_n_le_zero_is_a_silent_noop(fabe13):
+    # reference fabe13/fabe13.c:223; must not touch the pointers (nor need a GPU)
+    lib = fabe13._lib.load()
+    lib.fabe13_sincos(None, None, None, 0)
+    lib.fabe13_sincos(None, None, None, -5)
+    assert lib.fabe13_sincos_host(None, None, None, 0) == 0
+    assert lib.fabe13_sincos_device(None, None, None, 0, None) == 0
+
+
+def test_scalar_api_guards(fabe13):
+    # reference fabe13/fabe13.c:264-266
+    assert fabe13.sinc(0.0) == 1.0 and fabe13.sinc(5e-10) == 1.0
+    assert abs(fabe13.sinc(0.5) - np.sin(0.5) / 0.5) < 3e-16
+    assert np.isnan(fabe13.cot(0.0))          # sin == 0 -> NaN
+    assert abs(fabe13.tan(1.0) - np.tan(1.0)) < 1e-15
+    lib = fabe13._lib.load()
+    import math  # math.* call the platform libm, which is what the reference forwards to (fabe13/fabe13.c:267-269)
+
+    assert lib.fabe13_atan(0.3) == math.atan(0.3) and lib.fabe13_asin(0.3) == math.asin(0.3)
+    assert lib.fabe13_acos(0.3) == math.acos(0.3)
+    assert np.isnan(fabe13.sin(float("inf"))) and np.isnan(fabe13.cos(float("nan")))
+    assert fabe13.sin(0.0) == 0.0 and np.signbit(fabe13.sin(-0.0)) and fabe13.cos(-0.0) == 1.0

@@ -1,0 +1,77 @@
+"""The per-element algorithm (fabe13_b200/csrc/fabe13_core.h) is one piece of code compiled for the device and for
+the host.  These tests run its HOST instantiation (the implementation of the scalar API, reached in bulk through the
+fabe13_debug_host_core test hook) against the oracle, the golden vectors and exact quadrants -- so the algorithm is
+checked on every commit even where no GPU exists.  The `-m gpu` tests then check the device instantiation."""
+import numpy as np
+import pytest
+
+from parity import HUGE, QUALITY_TOL, bits, check_against_oracle, check_k, check_values
+
+CORES = [0, 1]
+
+
+@pytest.mark.parametrize("core", CORES)
+def test_golden_cases(fabe13, golden, core):
+    for name, g in golden.items():
+        s, c, k = fabe13.host_core(g["x"], core)
+        check_values(g["x"], s, c, g["ref_sin"], g["ref_cos"], g["libm_sin"], g["libm_cos"], label=f"{name}/core{core}")
+        check_k(g["x"], k, g["k_ref"], g["q_exact"], label=name)
+
+
+@pytest.mark.parametrize("core", CORES)
+def test_uniform_ranges_against_oracle(fabe13, oracle, core):
+    for seed, lo, hi in [(0xFABE1301, -np.pi, np.pi), (0xFABE1302, -1e4, 1e4), (0xFABE1303, -1e5 * np.pi, 1e5 * np.pi),
+                         (21, -1e6, 1e6), (22, -1e9, 1e9), (23, -3e13, 3e13)]:
+        x = oracle.fill_uniform(200_000, seed, lo, hi)
+        s, c, k = fabe13.host_core(x, core)
+        check_against_oracle(x, s, c, k, oracle, label=f"[{lo},{hi}] core{core}")
+
+
+@pytest.mark.parametrize("core", CORES)
+def test_extreme_range_against_libm(fabe13, oracle, core):
+    x = oracle.fill_loguniform(200_000, 0xFABE1304)
+    s, c, k = fabe13.host_core(x, core)
+    ls, lc = oracle.libm(x)
+    assert max(np.abs(s - ls).max(), np.abs(c - lc).max()) <= QUALITY_TOL
+    assert set(np.unique(k[np.abs(x) >= HUGE])) <= {0, 1, 2, 3}
+
+
+def test_payne_hanek_quadrants_are_exact(fabe13, oracle):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from gen_golden import q_exact  # exact big-integer rint(x*2/pi) mod 4
+
+    x = oracle.fill_loguniform(4000, 77)
+    x = x[np.abs(x) >= HUGE]
+    _, _, k = fabe13.host_core(x, 0)
+    want = np.array([q_exact(float(v)) for v in x])
+    assert np.array_equal(k, want)
+
+
+def test_scalar_api_is_the_array_core(fabe13, oracle):
+    x = np.concatenate([oracle.fill_uniform(300, 5, -50.0, 50.0), oracle.fill_loguniform(100, 6)])
+    s, c, _ = fabe13.host_core(x, 0)
+    for xi, si, ci in zip(x, s, c):
+        assert bits(np.array([fabe13.sin(xi)]))[0] == bits(np.array([si]))[0]
+        assert bits(np.array([fabe13.cos(xi)]))[0] == bits(np.array([ci]))[0]
+
+
+def test_scalar_api_deviates_from_reference_scalar_core_on_purpose(fabe13, oracle):
+    # reference fabe13_sin(1.0) = 0.8734 (SURVEY finding 2); ours is the correctly rounded neighbourhood of sin(1)
+    ref_s, _ = oracle.scalar_core(1.0)
+    assert abs(ref_s - np.sin(1.0)) > 3e-2
+    assert abs(fabe13.sin(1.0) - np.sin(1.0)) <= 1.2e-16
+
+
+def test_symmetry_bit_exact(fabe13, oracle):
+    x = np.concatenate([oracle.fill_uniform(50_000, 31, 0.0, 1e6), np.abs(oracle.fill_loguniform(50_000, 32))])
+    s, c, _ = fabe13.host_core(x, 0)
+    sn, cn, _ = fabe13.host_core(-x, 0)
+    assert np.array_equal(bits(sn), bits(-s)) and np.array_equal(bits(cn), bits(c))
+
+
+def test_pythagorean_identity(fabe13, oracle):
+    x = np.concatenate([oracle.fill_uniform(100_000, 41, -1e6, 1e6), oracle.fill_loguniform(100_000, 42)])
+    for core in CORES:
+        s, c, _ = fabe13.host_core(x, core)
+        assert np.abs(s * s + c * c - 1.0).max() <= 8e-16
