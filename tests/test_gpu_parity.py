@@ -1,0 +1,463 @@
+"""Parity tests proper: the CUDA path, called through the C ABI of libfabe13.so, against the oracle (the reference's
+algorithm restated on the CPU), the committed golden vectors (outputs of the reference itself) and libm.
+
+Covers the five BASELINE.json configs:
+  C1  N=1e6 uniform [-pi, pi]            C2  N=1e8 uniform [-1e4, 1e4]
+  C3  N=1e9 (size-independent properties + sampled oracle parity)
+  C4  extreme-range mix (Payne-Hanek worklist, sparse and dense)       C5  edge / special-value sweep, N = 10..1e6
+and every entry point: device pointers (+k hook, caller workspace), host pointers (pageable, pinned, legacy int-n
+entry), in-place, misaligned and mutually mis-congruent pointers, every unroll / vector-width / core variant.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from parity import HUGE, QNAN, QUALITY_TOL, bits, check_against_oracle, check_k, check_values
+
+pytestmark = pytest.mark.gpu
+
+SEED_C1, SEED_C2, SEED_C3, SEED_C4, SEED_C5 = 0xFABE1301, 0xFABE1302, 0xFABE1303, 0xFABE1304, 0xFABE1305
+
+
+def gpu_sincos_k(fabe13, cuda, x):
+    import torch
+
+    xt = torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+    s, c, k = fabe13.sincos_k(xt)
+    torch.cuda.synchronize()
+    return s.cpu().numpy(), c.cpu().numpy(), k.cpu().numpy()
+
+
+def gpu_sincos(fabe13, cuda, x):
+    import torch
+
+    xt = torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+    s, c = fabe13.sincos(xt)
+    torch.cuda.synchronize()
+    return s.cpu().numpy(), c.cpu().numpy()
+
+
+@pytest.fixture(autouse=True)
+def _defaults(fabe13):
+    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "small_n", "worklist_shift")}
+    yield
+    for k, v in saved.items():
+        fabe13.set_option(k, v)
+
+
+def test_native_library_is_the_one_running(fabe13, cuda):
+    name = fabe13.implementation_name()
+    assert name.startswith("CUDA sm_100") and "SMs" in name, name
+    before = fabe13.get_option("launches")
+    gpu_sincos(fabe13, cuda, np.linspace(-3, 3, 100_000))
+    assert fabe13.get_option("launches") > before  # our kernels launched, not a fallback
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors: outputs of the reference itself
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("core", [0, 1])
+def test_golden_vectors(fabe13, cuda, golden, core):
+    fabe13.set_option("core", core)
+    for name, g in golden.items():
+        s, c, k = gpu_sincos_k(fabe13, cuda, g["x"])
+        check_values(g["x"], s, c, g["ref_sin"], g["ref_cos"], g["libm_sin"], g["libm_cos"], label=f"{name}/core{core}")
+        check_k(g["x"], k, g["k_ref"], g["q_exact"], label=name)
+
+
+def test_golden_vectors_through_the_streaming_kernel(fabe13, cuda, golden):
+    """The golden cases are small and would all take the inline small-n kernel; force the streaming kernel +
+    worklist second pass over the concatenation of all cases as well."""
+    fabe13.set_option("small_n", 0)
+    names = sorted(golden)
+    x = np.concatenate([golden[n]["x"] for n in names])
+    cat = lambda key: np.concatenate([golden[n][key] for n in names])
+    for unroll in (1, 2, 4):
+        fabe13.set_option("unroll", unroll)
+        s, c, k = gpu_sincos_k(fabe13, cuda, x)
+        check_values(x, s, c, cat("ref_sin"), cat("ref_cos"), cat("libm_sin"), cat("libm_cos"), label=f"unroll{unroll}")
+        check_k(x, k, cat("k_ref"), cat("q_exact"), label=f"unroll{unroll}")
+
+
+def test_device_matches_host_instantiation_bit_for_bit(fabe13, cuda, oracle, golden):
+    """One algorithm, two compilers: the device lanes and the host scalar API must agree in every bit."""
+    x = np.concatenate([g["x"] for g in golden.values()] + [oracle.fill_uniform(200_000, 3, -1e6, 1e6),
+                                                             oracle.fill_loguniform(200_000, 4)])
+    for core in (0, 1):
+        fabe13.set_option("core", core)
+        s, c, k = gpu_sincos_k(fabe13, cuda, x)
+        hs, hc, hk = fabe13.host_core(x, core)
+        assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc)) and np.array_equal(k, hk)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C1 / C2: uniform ranges against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def test_c1_uniform_pi_1e6(fabe13, cuda, oracle):
+    x = oracle.fill_uniform(1_000_000, SEED_C1, -np.pi, np.pi)
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)
+    check_against_oracle(x, s, c, k, oracle, label="C1")
+
+
+@pytest.mark.parametrize("core", [0, 1])
+def test_reference_benchmark_range_1e5pi(fabe13, cuda, oracle, core):
+    fabe13.set_option("core", core)
+    x = oracle.fill_uniform(2_000_000, 0xBE, -1e5 * np.pi, 1e5 * np.pi)  # benchmark_fabe13.c:192
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)
+    check_against_oracle(x, s, c, k, oracle, label="bench-range")
+
+
+def test_c2_uniform_1e4_1e8_device_generated(fabe13, cuda, oracle):
+    """Full C2 size; inputs generated on the device by the same counter-based generator as the oracle's."""
+    import torch
+
+    n = 100_000_000
+    x = torch.empty(n, dtype=torch.float64, device=cuda)
+    fabe13.fill_uniform_device(x, SEED_C2, -1e4, 1e4)
+    s, c, k = fabe13.sincos_k(x)
+    torch.cuda.synchronize()
+    # the device generator reproduces the host generator bit for bit (checked on a window)
+    w0, w1 = 12_345_678, 12_345_678 + 2_000_000
+    xw = x[w0:w1].cpu().numpy()
+    assert np.array_equal(bits(xw), bits(oracle.fill_uniform(w1 - w0, SEED_C2, -1e4, 1e4, first_index=w0)))
+    check_against_oracle(xw, s[w0:w1].cpu().numpy(), c[w0:w1].cpu().numpy(), k[w0:w1].cpu().numpy(), oracle, label="C2 window")
+    # strided sample over the whole array
+    idx = torch.arange(0, n, 997, device=cuda)
+    xs = x[idx].cpu().numpy()
+    check_against_oracle(xs, s[idx].cpu().numpy(), c[idx].cpu().numpy(), k[idx].cpu().numpy(), oracle, label="C2 sample")
+    # size-independent property over all 1e8 elements
+    dev = (s * s + c * c - 1.0).abs().max().item()
+    assert dev <= 6e-16, dev
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C3: N = 1e9 on one GPU -- properties that do not need the oracle on every element, plus sampled oracle parity
+# ---------------------------------------------------------------------------------------------------------------
+def test_c3_1e9_properties(fabe13, cuda, oracle):
+    import torch
+
+    n = 1_000_000_000
+    x = torch.empty(n, dtype=torch.float64, device=cuda)
+    fabe13.fill_uniform_device(x, SEED_C3, -1e4, 1e4)
+    s, c = fabe13.sincos(x)
+    torch.cuda.synchronize()
+    # (1) Pythagorean identity, chunked to bound scratch memory
+    worst = 0.0
+    for b in range(0, n, 125_000_000):
+        sl = slice(b, b + 125_000_000)
+        worst = max(worst, (s[sl] * s[sl] + c[sl] * c[sl] - 1.0).abs().max().item())
+    assert worst <= 6e-16, worst
+    # (2) position independence: any slice recomputed on its own gives identical bits (sharding invariance)
+    for b, m in [(0, 1_000_000), (333_333_333, 1_000_001), (n - 999_999, 999_999)]:
+        s2, c2 = fabe13.sincos(x[b:b + m].clone())
+        assert torch.equal(s2.view(torch.int64), s[b:b + m].view(torch.int64))
+        assert torch.equal(c2.view(torch.int64), c[b:b + m].view(torch.int64))
+    # (3) odd/even symmetry, bit-exact
+    m = 10_000_000
+    sn, cn = fabe13.sincos(-x[:m])
+    assert torch.equal(sn.view(torch.int64), (-s[:m]).view(torch.int64)) and torch.equal(cn.view(torch.int64), c[:m].view(torch.int64))
+    # (4) oracle parity on a strided sample and on the two ends
+    idx = torch.cat([torch.arange(0, n, 4999, device=cuda), torch.arange(n - 100_000, n, device=cuda)])
+    xs = x[idx].cpu().numpy()
+    check_against_oracle(xs, s[idx].cpu().numpy(), c[idx].cpu().numpy(), None, oracle, label="C3 sample")
+    first = idx[:1000].cpu().numpy()
+    assert np.array_equal(bits(xs[:1000]), bits(np.array([oracle.fill_uniform(1, SEED_C3, -1e4, 1e4, first_index=int(i))[0] for i in first])))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C4: extreme-range mix -- the Payne-Hanek worklist (sparse), its overflow rescan (dense) and the inline kernel
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("core", [0, 1])
+def test_c4_dense_loguniform(fabe13, cuda, oracle, core):
+    fabe13.set_option("core", core)
+    n = 4_000_000
+    x = oracle.fill_loguniform(n, SEED_C4)
+    assert (np.abs(x) >= HUGE).mean() > 0.9
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)     # ~95% of lanes: worklist fills, the rest goes through the rescan
+    ls, lc = oracle.libm(x)
+    assert max(np.abs(s - ls).max(), np.abs(c - lc).max()) <= QUALITY_TOL
+    hs, hc, hk = fabe13.host_core(x, core)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc)) and np.array_equal(k, hk)
+
+
+def test_c4_sparse_mix_uses_the_worklist(fabe13, cuda, oracle):
+    n = 8_000_000
+    x = oracle.fill_uniform(n, SEED_C2, -1e4, 1e4)
+    h = oracle.fill_loguniform(n, SEED_C4)
+    sel = (np.arange(n) % 100) == 37            # 1% of lanes replaced by extreme values
+    x[sel] = h[sel]
+    x[5] = np.inf
+    x[6] = np.nan
+    x[7] = -0.0
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)
+    check_against_oracle(x, s, c, k, oracle, label="C4 sparse")
+    big = np.abs(x) >= HUGE
+    _, _, hk = fabe13.host_core(x[big & np.isfinite(x)], 0)
+    assert np.array_equal(k[big & np.isfinite(x)], hk)
+
+
+@pytest.mark.parametrize("shift", [0, 3, 20])
+def test_worklist_capacity_and_overflow(fabe13, cuda, oracle, shift):
+    """worklist_shift=20 leaves room for only 1024 entries: everything else must come out of the rescan pass;
+    shift=0 holds every lane.  Results are identical either way."""
+    fabe13.set_option("worklist_shift", shift)
+    n = 3_000_001
+    x = oracle.fill_uniform(n, 9, -1e6, 1e6)
+    h = oracle.fill_loguniform(n, 10)
+    sel = (np.arange(n) % 7) == 3
+    x[sel] = h[sel]
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)
+    hs, hc, hk = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc)) and np.array_equal(k, hk)
+
+
+def test_caller_provided_workspace(fabe13, cuda, oracle):
+    import torch
+
+    lib = fabe13._lib.load()
+    n = 2_000_000
+    x = oracle.fill_uniform(n, 19, -1e5, 1e5)
+    x[::1000] = oracle.fill_loguniform(n // 1000, 20)
+    xt = torch.from_numpy(x).to(cuda)
+    s = torch.empty_like(xt)
+    c = torch.empty_like(xt)
+    need = lib.fabe13_sincos_workspace_bytes(n)
+    ws = torch.empty(need, dtype=torch.uint8, device=cuda)
+    rc = lib.fabe13_sincos_device_ws(xt.data_ptr(), s.data_ptr(), c.data_ptr(), n, ws.data_ptr(), need,
+                                     torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    check_against_oracle(x, s.cpu().numpy(), c.cpu().numpy(), None, oracle, label="caller workspace")
+    # too small a workspace is refused loudly, not silently accepted
+    rc = lib.fabe13_sincos_device_ws(xt.data_ptr(), s.data_ptr(), c.data_ptr(), n, ws.data_ptr(), 64, None)
+    assert rc != 0 and lib.fabe13_cuda_last_error() != 0
+    lib.fabe13_cuda_clear_error()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C5: edge / special-value sweep at N = 10 .. 1e6
+# ---------------------------------------------------------------------------------------------------------------
+def edge_pattern(golden, n):
+    pool = np.concatenate([golden["specials"]["x"], golden["pio2_multiples_small"]["x"], golden["pio2_multiples_large"]["x"],
+                           golden["pio4_odd_multiples"]["x"],
+                           np.ldexp(1.0, -np.arange(1000, 1075)).astype(np.float64)])  # subnormal ramp
+    reps = (n + pool.size - 1) // pool.size
+    return np.tile(pool, reps)[:n].copy()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 31, 32, 33, 100, 1000, 10_000, 16_383, 16_384, 16_385, 100_000, 1_000_000])
+def test_c5_edge_sweep(fabe13, cuda, oracle, golden, n):
+    x = edge_pattern(golden, n)
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)
+    check_against_oracle(x, s, c, k, oracle, label=f"C5 n={n}")
+    hs, hc, hk = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc)) and np.array_equal(k, hk)
+
+
+def test_nan_payloads_and_signs_are_canonicalised(fabe13, cuda):
+    x = np.array([0x7FF0000000000001, 0xFFF8000000001234, 0x7FFFFFFFFFFFFFFF, 0xFFF0000000000000, 0x7FF0000000000000] * 20_000,
+                 dtype=np.uint64).view(np.float64)
+    for small_n in (0, 1 << 30):  # streaming kernel, inline kernel
+        fabe13.set_option("small_n", small_n)
+        s, c = gpu_sincos(fabe13, cuda, x)
+        assert np.all(bits(s) == QNAN) and np.all(bits(c) == QNAN)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pointers: alignment, congruence, in-place
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("off_in,off_s,off_c", [(0, 0, 0), (1, 1, 1), (2, 2, 2), (3, 3, 3), (1, 3, 1), (0, 2, 0), (0, 1, 2), (3, 0, 1)])
+def test_misaligned_and_incongruent_pointers(fabe13, cuda, oracle, off_in, off_s, off_c):
+    """Element offsets relative to a 256-byte-aligned allocation: equal offsets keep the 256-bit path with a peeled
+    head; offsets that agree only mod 2 fall to 128-bit vectors; otherwise 64-bit accesses."""
+    import torch
+
+    n = 300_007
+    fabe13.set_option("small_n", 0)
+    x = oracle.fill_uniform(n, 55, -1e5, 1e5)
+    x[1234] = 1e300
+    x[n - 1] = -1e250
+    x[0] = 3e200
+    bx = torch.zeros(n + 8, dtype=torch.float64, device=cuda)
+    bs = torch.full((n + 8,), 7.0, dtype=torch.float64, device=cuda)
+    bc = torch.full((n + 8,), 7.0, dtype=torch.float64, device=cuda)
+    bx[off_in:off_in + n] = torch.from_numpy(x).to(cuda)
+    fabe13.sincos(bx[off_in:off_in + n], out_sin=bs[off_s:off_s + n], out_cos=bc[off_c:off_c + n])
+    torch.cuda.synchronize()
+    s = bs[off_s:off_s + n].cpu().numpy()
+    c = bc[off_c:off_c + n].cpu().numpy()
+    hs, hc, _ = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
+    # nothing written outside the n elements
+    for buf, off in ((bs, off_s), (bc, off_c)):
+        out = torch.cat([buf[:off], buf[off + n:]]).cpu().numpy()
+        assert np.all(out == 7.0)
+
+
+def test_in_place(fabe13, cuda, oracle):
+    import torch
+
+    n = 1_000_003
+    x = oracle.fill_uniform(n, 56, -1e6, 1e6)
+    x[::500] = oracle.fill_loguniform((n + 499) // 500, 57)
+    xt = torch.from_numpy(x).to(cuda)
+    c = torch.empty_like(xt)
+    fabe13.sincos(xt, out_sin=xt, out_cos=c)  # in == sin_out
+    torch.cuda.synchronize()
+    hs, hc, _ = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(xt.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
+
+
+@pytest.mark.parametrize("blocks_per_sm", [1, 3, 8])
+def test_grid_size_does_not_change_results(fabe13, cuda, oracle, blocks_per_sm):
+    fabe13.set_option("blocks_per_sm", blocks_per_sm)
+    x = oracle.fill_uniform(5_000_011, 58, -1e4, 1e4)
+    s, c = gpu_sincos(fabe13, cuda, x)
+    hs, hc, _ = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-pointer entry points (the reference's own signature)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [10, 1000, 131_072, 1_000_000, 9_999_999])
+def test_host_pageable(fabe13, oracle, cuda, n):
+    x = oracle.fill_uniform(n, 60 + n % 7, -1e6, 1e6)
+    if n > 100:
+        x[17] = 1e200
+        x[n - 3] = np.nan
+    s, c = fabe13.sincos(x)  # numpy arrays: pageable memory, staged through pinned buffers
+    check_against_oracle(x, s, c, None, oracle, label=f"host pageable n={n}")
+
+
+@pytest.mark.parametrize("n", [10, 1_000_000, 30_000_001])
+def test_host_pinned(fabe13, oracle, cuda, n):
+    px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
+    px.array[:] = oracle.fill_uniform(n, 70, -1e4, 1e4)
+    fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)
+    m = min(n, 2_000_000)
+    check_against_oracle(px.array[:m], ps.array[:m], pc.array[:m], None, oracle, label="host pinned head")
+    check_against_oracle(px.array[-m:], ps.array[-m:], pc.array[-m:], None, oracle, label="host pinned tail")
+    hs, hc, _ = fabe13.host_core(px.array, 0)
+    assert np.array_equal(bits(ps.array), bits(hs)) and np.array_equal(bits(pc.array), bits(hc))
+    for p in (px, ps, pc):
+        p.free()
+
+
+def test_legacy_entry_point_int_n(fabe13, oracle, cuda):
+    """void fabe13_sincos(const double*, double*, double*, int) -- reference fabe13/fabe13.h:51-56 -- with host
+    pointers and with device pointers."""
+    import torch
+
+    n = 123_457
+    x = oracle.fill_uniform(n, 80, -1e5 * np.pi, 1e5 * np.pi)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    fabe13.sincos_legacy(x, s, c)
+    check_against_oracle(x, s, c, None, oracle, label="legacy host")
+    xt = torch.from_numpy(x).to(cuda)
+    st = torch.empty_like(xt)
+    ct = torch.empty_like(xt)
+    fabe13.sincos_legacy(xt, st, ct)  # synchronous by contract
+    assert np.array_equal(bits(st.cpu().numpy()), bits(s)) and np.array_equal(bits(ct.cpu().numpy()), bits(c))
+
+
+def test_reference_example_test_inputs_via_legacy_entry(fabe13, golden, cuda):
+    """The inputs of the reference's tests/test_fabe13.c (:107-112 scalars through the scalar API, :200-202 the
+    100-element ramp through fabe13_sincos) give libm-accurate answers -- including the elements the reference's own
+    scalar core gets wrong by 1e-2."""
+    g = golden["reference_test_inputs"]
+    x = g["x"]
+    for xi, ls, lc in zip(x[:20], g["libm_sin"][:20], g["libm_cos"][:20]):
+        s, c = fabe13.sin(float(xi)), fabe13.cos(float(xi))
+        if np.isfinite(xi):
+            assert abs(s - ls) <= 2e-16 and abs(c - lc) <= 2e-16
+        else:
+            assert np.isnan(s) and np.isnan(c)
+    ramp = np.ascontiguousarray(x[20:])
+    s = np.empty_like(ramp)
+    c = np.empty_like(ramp)
+    fabe13.sincos_legacy(ramp, s, c)
+    assert np.abs(s - g["libm_sin"][20:]).max() <= 2e-16 and np.abs(c - g["libm_cos"][20:]).max() <= 2e-16
+
+
+def test_mixed_host_device_pointers_fail_loudly(fabe13, cuda):
+    import torch
+
+    lib = fabe13._lib.load()
+    x = np.zeros(64)
+    d = torch.zeros(64, dtype=torch.float64, device=cuda)
+    rc = lib.fabe13_sincos_host(x.ctypes.data, d.data_ptr(), d.data_ptr(), 64)
+    assert rc != 0 and lib.fabe13_cuda_last_error() != 0
+    lib.fabe13_cuda_clear_error()
+
+
+def test_streams_and_concurrency(fabe13, cuda, oracle):
+    """The device entry is stream-ordered: two streams, interleaved launches, no host synchronisation in between."""
+    import torch
+
+    x1 = torch.from_numpy(oracle.fill_uniform(2_000_000, 90, -1e4, 1e4)).to(cuda)
+    x2 = torch.from_numpy(oracle.fill_loguniform(2_000_000, 91)).to(cuda)
+    st1, st2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(st1):
+            outs.append(fabe13.sincos(x1))
+        with torch.cuda.stream(st2):
+            outs.append(fabe13.sincos(x2))
+    torch.cuda.synchronize()
+    h1 = fabe13.host_core(x1.cpu().numpy(), 0)
+    h2 = fabe13.host_core(x2.cpu().numpy(), 0)
+    for i, (s, c) in enumerate(outs):
+        hs, hc, _ = h1 if i % 2 == 0 else h2
+        assert np.array_equal(bits(s.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
+
+
+def test_multi_entry_single_device(fabe13, cuda, oracle):
+    """fabe13_sincos_multi with the slices of one array (all on device 0 here; one device per slice on a multi-GPU
+    box -- see test_multi_entry_all_devices)."""
+    import torch
+
+    lib = fabe13._lib.load()
+    n = 1_000_001
+    x = oracle.fill_uniform(n, 95, -1e4, 1e4)
+    xt = torch.from_numpy(x).to(cuda)
+    s = torch.empty_like(xt)
+    c = torch.empty_like(xt)
+    world = 3
+    bounds = [fabe13.shard_bounds(n, world, r) for r in range(world)]
+    arr = lambda vals, t: (t * world)(*vals)
+    devs = arr([0] * world, ctypes.c_int)
+    pin = arr([xt.data_ptr() + 8 * b for b, _ in bounds], ctypes.c_void_p)
+    psn = arr([s.data_ptr() + 8 * b for b, _ in bounds], ctypes.c_void_p)
+    pcs = arr([c.data_ptr() + 8 * b for b, _ in bounds], ctypes.c_void_p)
+    cnt = arr([e - b for b, e in bounds], ctypes.c_size_t)
+    rc = lib.fabe13_sincos_multi(world, devs, pin, psn, pcs, cnt)
+    assert rc == 0
+    hs, hc, _ = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(s.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
+
+
+def test_multi_entry_all_devices(fabe13, cuda, oracle):
+    import torch
+
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("single-GPU box: fabe13_sincos_multi across devices not exercised")
+    lib = fabe13._lib.load()
+    n = 4_000_003
+    x = oracle.fill_uniform(n, 96, -1e4, 1e4)
+    bounds = [fabe13.shard_bounds(n, ndev, r) for r in range(ndev)]
+    xs = [torch.from_numpy(x[b:e]).to(f"cuda:{g}") for g, (b, e) in enumerate(bounds)]
+    ss = [torch.empty_like(t) for t in xs]
+    cs = [torch.empty_like(t) for t in xs]
+    arr = lambda vals, t: (t * ndev)(*vals)
+    rc = lib.fabe13_sincos_multi(ndev, arr(list(range(ndev)), ctypes.c_int), arr([t.data_ptr() for t in xs], ctypes.c_void_p),
+                                 arr([t.data_ptr() for t in ss], ctypes.c_void_p), arr([t.data_ptr() for t in cs], ctypes.c_void_p),
+                                 arr([t.numel() for t in xs], ctypes.c_size_t))
+    assert rc == 0
+    hs, hc, _ = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(np.concatenate([t.cpu().numpy() for t in ss])), bits(hs))
+    assert np.array_equal(bits(np.concatenate([t.cpu().numpy() for t in cs])), bits(hc))
