@@ -3,18 +3,20 @@
 // Replaces the reference's SIMD array drivers fabe13_sincos_avx512 / _avx2 / _neon (fabe13/fabe13.c:545-614,
 // :469-541, :399-464) and their scalar tail loops (:339-358).  Three kernels:
 //
-//   sincos_stream_kernel   the hot path.  Persistent grid-stride loop; each thread streams 256-bit vectors
-//                          (LDG.E.NA.256 in, two STG.E.EF.256 out), UNROLL vectors in flight.  Per lane:
-//                          reference-exact k, Cody-Waite, polynomial/Psi core, integer-pipe fix-up.  24 B/element
-//                          of HBM traffic, no shared memory.  Lanes with |x| >= 2^45 are found with a warp
-//                          ballot, stash x in their sin slot and append their index to a compacted worklist.
-//   sincos_worklist_kernel second pass: one Payne-Hanek reduction per worklist entry, lanes densely packed.
-//   sincos_rescan_kernel   only does work if the worklist overflowed: rescans the sin array for stashed
-//                          arguments (a finite value >= 2^45 can never be a sine) and reduces them in place.
-//   sincos_inline_kernel   small n: one launch, every path inline.
+//   sincos_stream_kernel      the hot path.  Grid-stride loop over tiles of 256*UNROLL 256-bit vectors, tiles taken
+//                             in address order (by default one tile per block, so DRAM sees one advancing window);
+//                             each thread issues LDG.E.NA.256 for its vectors, then two STG.E.EF.256 per vector.
+//                             Per lane: reference-exact k, Cody-Waite, polynomial/Psi core, integer-pipe fix-up.
+//                             24 B/element of HBM traffic, no shared memory.  Lanes with |x| >= 2^45 are found with
+//                             a warp ballot, stash x in their sin slot and append their index to a compacted,
+//                             segmented worklist (one atomic per warp that has any).
+//   sincos_second_pass_kernel one Payne-Hanek reduction per worklist entry, lanes densely packed; if a worklist
+//                             segment overflowed it also rescans the sin array for stashed arguments (a finite
+//                             value >= 2^45 can never be a sine) and reduces those in place.
+//   sincos_inline_kernel      small n: one launch, every path inline.
 //
 // Data layout in HBM: three contiguous FP64 arrays (in, sin, cos), optional int64 k array (test hook), and a
-// workspace = { u32 count, pad to 32 B, u32 entries[cap] }.
+// workspace = { kSegments counters, 128 B apart } { kSegments x seg_cap u32 element indices }.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,21 +27,30 @@ namespace fabe13 {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kWorklistHeaderBytes = 32;
+// Worklist segments: blocks append to segment blockIdx % kSegments, so same-address atomics (which serialise in
+// L2) are spread over kSegments counters placed one 128-byte line apart.
+constexpr int kSegments = 32;
+constexpr int kCounterStrideWords = 32;
+constexpr int kWorklistHeaderBytes = kSegments * kCounterStrideWords * 4;
 
 __constant__ uint64_t c_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
+
+struct Worklist {
+    unsigned int* counters;  // kSegments counters, kCounterStrideWords apart; may exceed seg_cap (= overflow)
+    uint32_t* entries;       // segment s owns entries[s*seg_cap, (s+1)*seg_cap)
+    uint32_t seg_cap;
+};
 
 struct StreamArgs {
     const double* in;
     double* sin_out;
     double* cos_out;
-    long long* k_out;           // null unless WITH_K
-    uint32_t n;                 // elements in this launch (<= 2^31)
-    uint32_t head;              // scalar elements before the vector body
-    uint32_t nvec;              // vectors in the body
-    unsigned int* wl_count;     // worklist header
-    uint32_t* wl_entries;
-    uint32_t wl_cap;
+    long long* k_out;  // null unless WITH_K
+    uint32_t n;        // elements in this launch (<= 2^31)
+    uint32_t head;     // scalar elements before the vector body
+    uint32_t nvec;     // vectors in the body
+    uint32_t ntiles;   // tiles of kThreads*UNROLL vectors
+    Worklist wl;
 };
 
 // ---- 64/128/256-bit streaming accesses.  Loads do not allocate in L1 (each byte is read once); stores are
@@ -95,36 +106,40 @@ __device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& c
     return huge;
 }
 
-// Append the flagged lanes of this warp to the worklist (one atomic per warp per call).
-__device__ __forceinline__ void worklist_push(bool flag, uint32_t index, const StreamArgs& a, uint32_t lane) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
-    if (m == 0) return;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(a.wl_count, (unsigned)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (flag) {
-        const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-        if (slot < a.wl_cap) a.wl_entries[slot] = index;
+// Append this warp's flagged elements (`mine` per lane, indices produced by `emit`) to the block's worklist segment:
+// a warp prefix sum, one atomic for the whole warp, then each lane writes its own run of slots.
+template <typename Emit>
+__device__ __forceinline__ void worklist_push(uint32_t mine, const Worklist& wl, uint32_t lane, Emit emit) {
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += t;
     }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return;
+    const uint32_t seg = blockIdx.x % kSegments;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(wl.counters + seg * kCounterStrideWords, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    emit(wl.entries + (size_t)seg * wl.seg_cap, base + incl - mine);
 }
 
 template <int CORE, int VEC, int UNROLL, bool WITH_K>
 __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x;
-    const uint32_t stride = gridDim.x * kThreads;
     const double* in = a.in + a.head;
     double* so = a.sin_out + a.head;
     double* co = a.cos_out + a.head;
 
-    // warp-uniform trip count so that the ballots below always see a full warp
-    for (uint32_t wbase = gtid - lane; wbase < a.nvec; wbase += UNROLL * stride) {
+    // grid-stride over tiles; the trip count is block-uniform, so the ballots below always see full warps
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
         uint64_t xb[UNROLL][VEC];
         bool live[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t v = wbase + lane + u * stride;
+            const uint32_t v = v0 + u * kThreads;
             live[u] = v < a.nvec;
             if (live[u]) {
                 load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
@@ -133,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
                 for (int j = 0; j < VEC; ++j) xb[u][j] = 0;
             }
         }
-        bool any_huge = false;
+        uint32_t n_huge = 0;
         uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
         long long kk[UNROLL][VEC];
         bool huge[UNROLL][VEC];
@@ -141,14 +156,14 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                huge[u][j] = fast_lane<CORE>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
-                any_huge |= huge[u][j];
+                huge[u][j] = fast_lane<CORE>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);  // xb == 0 when !live: never huge
+                n_huge += huge[u][j] ? 1u : 0u;
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             if (live[u]) {
-                const size_t e = (size_t)(wbase + lane + u * stride) * VEC;
+                const size_t e = (size_t)(v0 + u * kThreads) * VEC;
                 store_stream<VEC>(so + e, sb[u]);
                 store_stream<VEC>(co + e, cb[u]);
                 if (WITH_K) {
@@ -157,15 +172,19 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
                 }
             }
         }
-        if (__any_sync(0xFFFFFFFFu, any_huge)) {  // rare: compact the Payne-Hanek lanes
+        if (__any_sync(0xFFFFFFFFu, n_huge != 0)) {  // rare: compact the Payne-Hanek lanes of this warp
+            worklist_push(n_huge, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
+                for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const uint32_t idx = a.head + (wbase + lane + u * stride) * VEC + j;
-                    worklist_push(huge[u][j] && live[u], idx, a, lane);
+                    for (int j = 0; j < VEC; ++j) {
+                        if (huge[u][j]) {
+                            if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
+                            ++slot;
+                        }
+                    }
                 }
-            }
+            });
         }
     }
 
@@ -178,13 +197,15 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
         uint64_t xb = 0, sb, cb;
         long long k;
         if (on) xb = (uint64_t)__double_as_longlong(a.in[idx]);
-        const bool huge = fast_lane<CORE>(xb, sb, cb, k) && on;
+        const bool huge = fast_lane<CORE>(xb, sb, cb, k);
         if (on) {
             a.sin_out[idx] = __longlong_as_double((long long)sb);
             a.cos_out[idx] = __longlong_as_double((long long)cb);
             if (WITH_K) a.k_out[idx] = k;
         }
-        worklist_push(huge, idx, a, lane);
+        worklist_push(huge ? 1u : 0u, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
+            if (huge && slot < a.wl.seg_cap) seg_entries[slot] = idx;
+        });
     }
 }
 
@@ -193,9 +214,7 @@ struct SecondPassArgs {
     double* cos_out;
     long long* k_out;
     uint32_t n;
-    const unsigned int* wl_count;
-    const uint32_t* wl_entries;
-    uint32_t wl_cap;
+    Worklist wl;
 };
 
 template <int CORE>
@@ -213,32 +232,51 @@ __device__ __forceinline__ void stage_table(uint64_t* table) {
     __syncthreads();
 }
 
-// Second pass over the compacted worklist: every active lane runs Payne-Hanek.  The 2/pi table is staged in
+// Second pass.  (1) The compacted worklist: every active lane runs Payne-Hanek.  The 2/pi table is staged in
 // shared memory because lanes index it by their own exponent (a divergent __constant__ read would serialise).
+// (2) Only if some segment overflowed: rescan the sin array for arguments still stashed there.  Entries already
+// reduced in (1) no longer look like stashed arguments; one reduced twice by a race gets the same bits twice.
 template <int CORE>
-__global__ void __launch_bounds__(kThreads) sincos_worklist_kernel(const SecondPassArgs a) {
+__global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const SecondPassArgs a) {
     __shared__ uint64_t table[FABE13_PH_WORDS];
-    const uint32_t total = *a.wl_count;
-    if (total == 0) return;
-    stage_table(table);
-    const uint32_t cnt = total < a.wl_cap ? total : a.wl_cap;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) {
-        const uint32_t idx = a.wl_entries[i];
+    __shared__ uint32_t seg_start[kSegments + 1];
+    __shared__ int overflowed;
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        const uint32_t raw = a.wl.counters[lane * kCounterStrideWords];
+        const bool over = raw > a.wl.seg_cap;
+        uint32_t incl = over ? a.wl.seg_cap : raw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        seg_start[lane + 1] = incl;
+        if (lane == 0) seg_start[0] = 0;
+        const unsigned any_over = __ballot_sync(0xFFFFFFFFu, over);
+        if (lane == 0) overflowed = any_over != 0;
+    }
+    stage_table(table);  // includes the __syncthreads that publishes seg_start / overflowed
+    const uint32_t total = seg_start[kSegments];
+    if (total == 0 && !overflowed) return;
+
+    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = gtid; i < total; i += stride) {
+        uint32_t seg = 0;  // largest seg with seg_start[seg] <= i
+#pragma unroll
+        for (int step = kSegments / 2; step > 0; step >>= 1)
+            if (seg_start[seg + step] <= i) seg += step;
+        const uint32_t idx = a.wl.entries[(size_t)seg * a.wl.seg_cap + (i - seg_start[seg])];
         const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[idx]);
         reduce_stashed<CORE>(a, idx, xb, table);
     }
-}
-
-// Overflow pass: lanes that found the worklist full are still stashed in the sin array.
-template <int CORE>
-__global__ void __launch_bounds__(kThreads) sincos_rescan_kernel(const SecondPassArgs a) {
-    __shared__ uint64_t table[FABE13_PH_WORDS];
-    if (*a.wl_count <= a.wl_cap) return;
-    stage_table(table);
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < a.n; i += gridDim.x * kThreads) {
-        const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[i]);
-        const uint32_t ahi = (uint32_t)(xb >> 32) & 0x7FFFFFFFu;
-        if ((ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD)) reduce_stashed<CORE>(a, i, xb, table);
+    if (overflowed) {
+        for (uint32_t i = gtid; i < a.n; i += stride) {
+            const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[i]);
+            const uint32_t ahi = (uint32_t)(xb >> 32) & 0x7FFFFFFFu;
+            if ((ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD)) reduce_stashed<CORE>(a, i, xb, table);
+        }
     }
 }
 
@@ -289,9 +327,9 @@ __global__ void __launch_bounds__(kThreads) fill_loguniform_kernel(double* out, 
 template <int CORE, int VEC, bool WITH_K>
 cudaError_t launch_stream_unroll(const StreamArgs& a, int unroll, int grid, cudaStream_t stream) {
     switch (unroll) {
-        case 1: sincos_stream_kernel<CORE, VEC, 1, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
+        case 2: sincos_stream_kernel<CORE, VEC, 2, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
         case 4: sincos_stream_kernel<CORE, VEC, 4, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
-        default: sincos_stream_kernel<CORE, VEC, 2, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
+        default: sincos_stream_kernel<CORE, VEC, 1, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
     }
     return cudaGetLastError();
 }
@@ -305,14 +343,20 @@ cudaError_t launch_stream_vec(const StreamArgs& a, int vec, int unroll, int grid
     }
 }
 
+uint32_t segment_capacity(size_t n, const LaunchTuning& t) {
+    size_t cap = n >> t.worklist_shift;
+    if (cap < 4096) cap = 4096;
+    return (uint32_t)((cap + kSegments - 1) / kSegments);
+}
+
 template <int CORE>
 cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
                         const LaunchTuning& t, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                         int* launches) {
     if (n < (size_t)t.small_n || workspace == nullptr) {
-        const int need = (int)((n + kThreads - 1) / kThreads);
-        const int cap = dev.sm_count * 8;
-        sincos_inline_kernel<CORE><<<need < cap ? need : cap, kThreads, 0, stream>>>(d_in, d_sin, d_cos, d_k, (uint32_t)n);
+        const long long need = (long long)((n + kThreads - 1) / kThreads);
+        const long long cap = (long long)dev.sm_count * 64;
+        sincos_inline_kernel<CORE><<<(int)(need < cap ? need : cap), kThreads, 0, stream>>>(d_in, d_sin, d_cos, d_k, (uint32_t)n);
         *launches += 1;
         return cudaGetLastError();
     }
@@ -330,6 +374,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     const uintptr_t vbytes = (uintptr_t)vec * 8;
     uint32_t head = (uint32_t)(((vbytes - (pi & (vbytes - 1))) & (vbytes - 1)) / 8);
     if (head > n) head = (uint32_t)n;
+    const int unroll = (t.unroll == 2 || t.unroll == 4) ? t.unroll : 1;
 
     StreamArgs a;
     a.in = d_in;
@@ -339,20 +384,21 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     a.n = (uint32_t)n;
     a.head = head;
     a.nvec = (uint32_t)((n - head) / vec);
-    a.wl_count = (unsigned int*)workspace;
-    a.wl_entries = (uint32_t*)((char*)workspace + kWorklistHeaderBytes);
-    a.wl_cap = (uint32_t)((workspace_bytes(n, t) - kWorklistHeaderBytes) / sizeof(uint32_t));
+    a.ntiles = (uint32_t)(((size_t)a.nvec + (size_t)kThreads * unroll - 1) / ((size_t)kThreads * unroll));
+    a.wl.counters = (unsigned int*)workspace;
+    a.wl.entries = (uint32_t*)((char*)workspace + kWorklistHeaderBytes);
+    a.wl.seg_cap = segment_capacity(n, t);
 
     cudaError_t err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
     if (err != cudaSuccess) return err;
 
-    const int unroll = (t.unroll == 1 || t.unroll == 4) ? t.unroll : 2;
-    const long long want = ((long long)a.nvec + (long long)kThreads * unroll - 1) / ((long long)kThreads * unroll);
-    const long long resident = (long long)dev.sm_count * t.blocks_per_sm;
-    int grid = (int)(want < resident ? want : resident);
+    // blocks_per_sm == 0: one tile per block (the block scheduler walks the array in address order);
+    // otherwise a persistent grid of SMs*blocks_per_sm blocks strides over the tiles.
+    long long grid = a.ntiles;
+    if (t.blocks_per_sm > 0 && grid > (long long)dev.sm_count * t.blocks_per_sm) grid = (long long)dev.sm_count * t.blocks_per_sm;
     if (grid < 1) grid = 1;
-    err = d_k ? launch_stream_vec<CORE, true>(a, vec, unroll, grid, stream)
-              : launch_stream_vec<CORE, false>(a, vec, unroll, grid, stream);
+    err = d_k ? launch_stream_vec<CORE, true>(a, vec, unroll, (int)grid, stream)
+              : launch_stream_vec<CORE, false>(a, vec, unroll, (int)grid, stream);
     if (err != cudaSuccess) return err;
 
     SecondPassArgs b;
@@ -360,22 +406,16 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     b.cos_out = d_cos;
     b.k_out = d_k;
     b.n = (uint32_t)n;
-    b.wl_count = a.wl_count;
-    b.wl_entries = a.wl_entries;
-    b.wl_cap = a.wl_cap;
-    const int grid2 = dev.sm_count * 4;
-    sincos_worklist_kernel<CORE><<<grid2, kThreads, 0, stream>>>(b);
-    sincos_rescan_kernel<CORE><<<grid2, kThreads, 0, stream>>>(b);
-    *launches += 3;
+    b.wl = a.wl;
+    sincos_second_pass_kernel<CORE><<<dev.sm_count * t.second_pass_blocks_per_sm, kThreads, 0, stream>>>(b);
+    *launches += 2;
     return cudaGetLastError();
 }
 
 }  // namespace
 
 size_t workspace_bytes(size_t n, const LaunchTuning& t) {
-    size_t cap = n >> t.worklist_shift;
-    if (cap < 1024) cap = 1024;
-    return (size_t)kWorklistHeaderBytes + cap * sizeof(uint32_t);
+    return (size_t)kWorklistHeaderBytes + (size_t)kSegments * segment_capacity(n, t) * sizeof(uint32_t);
 }
 
 cudaError_t fill_uniform(double* d_out, size_t n, uint64_t seed, uint64_t first, double lo, double hi,

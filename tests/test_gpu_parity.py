@@ -40,7 +40,7 @@ def gpu_sincos(fabe13, cuda, x):
 
 @pytest.fixture(autouse=True)
 def _defaults(fabe13):
-    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "small_n", "worklist_shift")}
+    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "second_pass_blocks_per_sm", "small_n", "worklist_shift")}
     yield
     for k, v in saved.items():
         fabe13.set_option(k, v)
@@ -246,7 +246,7 @@ def edge_pattern(golden, n):
     return np.tile(pool, reps)[:n].copy()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 10, 31, 32, 33, 100, 1000, 10_000, 16_383, 16_384, 16_385, 100_000, 1_000_000])
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 31, 32, 33, 100, 1000, 10_000, 100_000, 262_143, 262_144, 262_145, 1_000_000])
 def test_c5_edge_sweep(fabe13, cuda, oracle, golden, n):
     x = edge_pattern(golden, n)
     s, c, k = gpu_sincos_k(fabe13, cuda, x)
@@ -309,7 +309,7 @@ def test_in_place(fabe13, cuda, oracle):
     assert np.array_equal(bits(xt.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
 
 
-@pytest.mark.parametrize("blocks_per_sm", [1, 3, 8])
+@pytest.mark.parametrize("blocks_per_sm", [0, 1, 3, 8])
 def test_grid_size_does_not_change_results(fabe13, cuda, oracle, blocks_per_sm):
     fabe13.set_option("blocks_per_sm", blocks_per_sm)
     x = oracle.fill_uniform(5_000_011, 58, -1e4, 1e4)
