@@ -227,6 +227,12 @@ __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t
     if (a.k_out) a.k_out[idx] = k;
 }
 
+// 2^45 <= |v| < Inf: an argument parked in the sin array by the first pass (no sine has that magnitude)
+__device__ __forceinline__ bool is_stashed(uint64_t bits) {
+    const uint32_t ahi = (uint32_t)(bits >> 32) & 0x7FFFFFFFu;
+    return (ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD);
+}
+
 __device__ __forceinline__ void stage_table(uint64_t* table) {
     if (threadIdx.x < FABE13_PH_WORDS) table[threadIdx.x] = c_ph_table[threadIdx.x];
     __syncthreads();
@@ -234,8 +240,9 @@ __device__ __forceinline__ void stage_table(uint64_t* table) {
 
 // Second pass.  (1) The compacted worklist: every active lane runs Payne-Hanek.  The 2/pi table is staged in
 // shared memory because lanes index it by their own exponent (a divergent __constant__ read would serialise).
-// (2) Only if some segment overflowed: rescan the sin array for arguments still stashed there.  Entries already
-// reduced in (1) no longer look like stashed arguments; one reduced twice by a race gets the same bits twice.
+// (2) Only if some segment overflowed: rescan the sin array for arguments still stashed there.  (1) and (2) run
+// concurrently across blocks, so both check that the slot still holds a stashed argument; if two threads race on
+// one slot they read the same x and write the same bits.
 template <int CORE>
 __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const SecondPassArgs a) {
     __shared__ uint64_t table[FABE13_PH_WORDS];
@@ -269,13 +276,13 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
             if (seg_start[seg + step] <= i) seg += step;
         const uint32_t idx = a.wl.entries[(size_t)seg * a.wl.seg_cap + (i - seg_start[seg])];
         const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[idx]);
-        reduce_stashed<CORE>(a, idx, xb, table);
+        // still a stashed argument?  (when the rescan below is active another thread may already have reduced it)
+        if (is_stashed(xb)) reduce_stashed<CORE>(a, idx, xb, table);
     }
     if (overflowed) {
         for (uint32_t i = gtid; i < a.n; i += stride) {
             const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[i]);
-            const uint32_t ahi = (uint32_t)(xb >> 32) & 0x7FFFFFFFu;
-            if ((ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD)) reduce_stashed<CORE>(a, i, xb, table);
+            if (is_stashed(xb)) reduce_stashed<CORE>(a, i, xb, table);
         }
     }
 }

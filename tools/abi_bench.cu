@@ -1,0 +1,85 @@
+// abi_bench.cu -- latency / throughput of the C ABI entry points measured from C (no Python in the loop).
+//   nvcc -O2 -o tools/abi_bench tools/abi_bench.cu -Iinclude -Lfabe13_b200/lib -lfabe13 -Xlinker -rpath -Xlinker '$ORIGIN/../fabe13_b200/lib'
+// Prints, per n: wall time of fabe13_sincos_device + stream sync, GPU time between events, and the host-pointer
+// entry (pinned and pageable) wall time.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <chrono>
+#include <vector>
+
+#include "fabe13.h"
+#include "fabe13_cuda.h"
+
+static double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char** argv) {
+    const size_t nmax = argc > 1 ? (size_t)atoll(argv[1]) : (size_t)100000000;
+    double *d_in, *d_s, *d_c;
+    cudaMalloc(&d_in, nmax * 8);
+    cudaMalloc(&d_s, nmax * 8);
+    cudaMalloc(&d_c, nmax * 8);
+    fabe13_debug_fill_uniform_device(d_in, nmax, 0xFABE1305ull, 0, -1e4, 1e4, nullptr);
+    cudaDeviceSynchronize();
+    double* h_in = (double*)fabe13_cuda_host_alloc(nmax * 8);
+    double* h_s = (double*)fabe13_cuda_host_alloc(nmax * 8);
+    double* h_c = (double*)fabe13_cuda_host_alloc(nmax * 8);
+    cudaMemcpy(h_in, d_in, nmax * 8, cudaMemcpyDeviceToHost);
+    std::vector<double> p_in(h_in, h_in + nmax), p_s(nmax), p_c(nmax);
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    printf("%s\n", fabe13_get_active_implementation_name());
+    printf("%12s %14s %14s %14s %14s %16s %16s\n", "n", "dev wall us", "dev gpu us", "dev Gelem/s", "back2back us", "host pinned us", "host pageable us");
+    for (size_t n = 1; n <= nmax; n *= 10) {
+        const int reps = n <= 1000000 ? 200 : (n <= 10000000 ? 50 : 10);
+        for (int i = 0; i < 5; ++i) fabe13_sincos_device(d_in, d_s, d_c, n, st);
+        cudaStreamSynchronize(st);
+        double wall = 1e30, gpu = 1e30;
+        for (int i = 0; i < reps; ++i) {
+            const double t0 = now_us();
+            cudaEventRecord(e0, st);
+            fabe13_sincos_device(d_in, d_s, d_c, n, st);
+            cudaEventRecord(e1, st);
+            cudaStreamSynchronize(st);
+            const double t1 = now_us();
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (t1 - t0 < wall) wall = t1 - t0;
+            if (ms * 1e3 < gpu) gpu = ms * 1e3;
+        }
+        // back-to-back: queue `reps` calls, one sync: steady-state cost per call when the caller does not wait
+        const double t0 = now_us();
+        for (int i = 0; i < reps; ++i) fabe13_sincos_device(d_in, d_s, d_c, n, st);
+        cudaStreamSynchronize(st);
+        const double b2b = (now_us() - t0) / reps;
+        double hp = 1e30, hg = 1e30;
+        const int hreps = n <= 1000000 ? 20 : 3;
+        fabe13_sincos_host(h_in, h_s, h_c, n);
+        for (int i = 0; i < hreps; ++i) {
+            const double a = now_us();
+            fabe13_sincos_host(h_in, h_s, h_c, n);
+            const double b = now_us();
+            if (b - a < hp) hp = b - a;
+        }
+        fabe13_sincos_host(p_in.data(), p_s.data(), p_c.data(), n);
+        for (int i = 0; i < hreps; ++i) {
+            const double a = now_us();
+            fabe13_sincos_host(p_in.data(), p_s.data(), p_c.data(), n);
+            const double b = now_us();
+            if (b - a < hg) hg = b - a;
+        }
+        printf("%12zu %14.1f %14.1f %14.3f %14.1f %16.1f %16.1f\n", n, wall, gpu, n / gpu / 1e3, b2b, hp, hg);
+        fflush(stdout);
+        if (memcmp(h_s, p_s.data(), n * 8) != 0) printf("  !! pinned and pageable host paths disagree\n");
+    }
+    long long launches = 0;
+    fabe13_cuda_get_option("launches", &launches);
+    printf("kernel launches so far: %lld, last error %d\n", launches, fabe13_cuda_last_error());
+    return 0;
+}
