@@ -69,6 +69,8 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
+        self.power_w = []
+        self.reason_mask = 0
         self.reasons = set()
         self.max_mhz = None
         self._stop = threading.Event()
@@ -96,13 +98,15 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.reason_mask |= int(r)
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def start(self):
         if self.nv:
@@ -117,7 +121,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "sm_mhz_min": s[0] if s else None, "power_w_max": max(self.power_w) if self.power_w else None,
+                "reason_mask": hex(self.reason_mask)}
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -44,6 +44,32 @@
 
 enum { FABE13_CORE_POLY = 0, FABE13_CORE_PSI = 1 };
 
+// The FP64 constants of the hot path.  On the device they live in the constant bank, so every DFMA takes its
+// coefficient as a c[bank][offset] operand: no per-thread materialisation of 64-bit immediates (which costs ~50
+// UMOV/MOV per thread -- a lot when a thread handles only four elements).  On the host they are a static table.
+struct Fabe13Coef {
+    double k_hi, k_lo, magic, neg_magic;
+    double pio2_1, pio2_2, pio2_3;
+    double s1, s2, s3, s4, s5, s6;
+    double c1, c2, c3, c4, c5, c6;
+    double neg_half, one;
+};
+#define FABE13_COEF_INIT                                                                                             \
+    {                                                                                                                \
+        FABE13_K_TWO_OVER_PI_HI, FABE13_K_TWO_OVER_PI_LO, FABE13_ROUND_MAGIC, -FABE13_ROUND_MAGIC, -FABE13_PIO2_1,     \
+            -FABE13_PIO2_2, -FABE13_PIO2_3, FABE13_S1, FABE13_S2, FABE13_S3, FABE13_S4, FABE13_S5, FABE13_S6, FABE13_C1, \
+            FABE13_C2, FABE13_C3, FABE13_C4, FABE13_C5, FABE13_C6, -0.5, 1.0                                           \
+    }
+#if defined(__CUDACC__)
+static __constant__ Fabe13Coef fabe13_coef_device = FABE13_COEF_INIT;
+#endif
+static const Fabe13Coef fabe13_coef_host = FABE13_COEF_INIT;
+#if defined(__CUDA_ARCH__)
+#define FABE13_CF(field) (fabe13_coef_device.field)
+#else
+#define FABE13_CF(field) (fabe13_coef_host.field)
+#endif
+
 #define FABE13_QNAN_BITS 0x7FF8000000000000ull
 #define FABE13_ONE_BITS 0x3FF0000000000000ull
 #define FABE13_ABS_MASK 0x7FFFFFFFFFFFFFFFull
@@ -76,22 +102,22 @@ FABE13_HD double fabe13_from_bits(uint64_t u) {
 //    returns k as a double; *k_int receives k as an integer (valid for |k| < 2^51, i.e. far beyond the 2^45 cut)
 // ---------------------------------------------------------------------------------------------------------------
 FABE13_HD double fabe13_quadrant_index(double x, int64_t* k_int) {
-    const double p_hi = FABE13_MUL(x, FABE13_K_TWO_OVER_PI_HI);
-    const double e1 = FABE13_FMA(x, FABE13_K_TWO_OVER_PI_HI, -p_hi);
-    const double p_lo = FABE13_FMA(x, FABE13_K_TWO_OVER_PI_LO, e1);
+    const double p_hi = FABE13_MUL(x, FABE13_CF(k_hi));
+    const double e1 = FABE13_FMA(x, FABE13_CF(k_hi), -p_hi);
+    const double p_lo = FABE13_FMA(x, FABE13_CF(k_lo), e1);
     const double sum = FABE13_ADD(p_hi, p_lo);
     // rint() by the 1.5*2^52 bias: the biased sum carries k in its low mantissa bits (two's complement)
-    const double biased = FABE13_ADD(sum, FABE13_ROUND_MAGIC);
+    const double biased = FABE13_ADD(sum, FABE13_CF(magic));
     *k_int = (int64_t)(fabe13_bits(biased) - 0x4338000000000000ull);
-    return FABE13_ADD(biased, -FABE13_ROUND_MAGIC);
+    return FABE13_ADD(biased, FABE13_CF(neg_magic));
 }
 
 // 2a. Cody-Waite with a correct three-word pi/2.  x - k*P1 is exact (a multiple of 2^-52 below 2), the two
 //     following FMAs each round once.
 FABE13_HD double fabe13_cody_waite(double x, double k) {
-    double r = FABE13_FMA(k, -FABE13_PIO2_1, x);
-    r = FABE13_FMA(k, -FABE13_PIO2_2, r);
-    r = FABE13_FMA(k, -FABE13_PIO2_3, r);
+    double r = FABE13_FMA(k, FABE13_CF(pio2_1), x);  // the table holds the negated words
+    r = FABE13_FMA(k, FABE13_CF(pio2_2), r);
+    r = FABE13_FMA(k, FABE13_CF(pio2_3), r);
     return r;
 }
 
@@ -198,20 +224,20 @@ FABE13_HD double fabe13_payne_hanek(uint64_t abs_bits, const uint64_t* W, int* q
 // ---------------------------------------------------------------------------------------------------------------
 FABE13_HD void fabe13_core_poly(double r, double* s, double* c) {
     const double z = FABE13_MUL(r, r);
-    double ps = FABE13_FMA(z, FABE13_S6, FABE13_S5);
-    double pc = FABE13_FMA(z, FABE13_C6, FABE13_C5);
-    ps = FABE13_FMA(z, ps, FABE13_S4);
-    pc = FABE13_FMA(z, pc, FABE13_C4);
-    ps = FABE13_FMA(z, ps, FABE13_S3);
-    pc = FABE13_FMA(z, pc, FABE13_C3);
-    ps = FABE13_FMA(z, ps, FABE13_S2);
-    pc = FABE13_FMA(z, pc, FABE13_C2);
-    ps = FABE13_FMA(z, ps, FABE13_S1);
-    pc = FABE13_FMA(z, pc, FABE13_C1);
+    double ps = FABE13_FMA(z, FABE13_CF(s6), FABE13_CF(s5));
+    double pc = FABE13_FMA(z, FABE13_CF(c6), FABE13_CF(c5));
+    ps = FABE13_FMA(z, ps, FABE13_CF(s4));
+    pc = FABE13_FMA(z, pc, FABE13_CF(c4));
+    ps = FABE13_FMA(z, ps, FABE13_CF(s3));
+    pc = FABE13_FMA(z, pc, FABE13_CF(c3));
+    ps = FABE13_FMA(z, ps, FABE13_CF(s2));
+    pc = FABE13_FMA(z, pc, FABE13_CF(c2));
+    ps = FABE13_FMA(z, ps, FABE13_CF(s1));
+    pc = FABE13_FMA(z, pc, FABE13_CF(c1));
     const double rz = FABE13_MUL(r, z);
-    pc = FABE13_FMA(z, pc, -0.5);
+    pc = FABE13_FMA(z, pc, FABE13_CF(neg_half));
     *s = FABE13_FMA(rz, ps, r);
-    *c = FABE13_FMA(z, pc, 1.0);
+    *c = FABE13_FMA(z, pc, FABE13_CF(one));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -268,13 +294,14 @@ FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, unsigne
     uint64_t co = swap ? sb : cb;
     so ^= (uint64_t)(q & 2u) << 62;
     co ^= (uint64_t)((q + 1u) & 2u) << 62;
+    // overrides, merged into one select per output: tiny -> (x, 1); NaN/Inf -> (qNaN, qNaN)
     const uint64_t ax = x_bits & FABE13_ABS_MASK;
-    const bool tiny = ax <= FABE13_TINY_BITS;
     const bool special = ax >= FABE13_INF_BITS;
-    so = tiny ? x_bits : so;
-    co = tiny ? FABE13_ONE_BITS : co;
-    so = special ? FABE13_QNAN_BITS : so;
-    co = special ? FABE13_QNAN_BITS : co;
+    const bool override_ = special || ax <= FABE13_TINY_BITS;
+    const uint64_t alt_s = special ? FABE13_QNAN_BITS : x_bits;
+    const uint64_t alt_c = special ? FABE13_QNAN_BITS : FABE13_ONE_BITS;
+    so = override_ ? alt_s : so;
+    co = override_ ? alt_c : co;
     *s_bits = so;
     *c_bits = co;
 }

@@ -140,5 +140,23 @@ int main(int argc, char** argv) {
     run<LD_NA, ST_CS, 1, 2, 24>("1R2W +24 DFMA unroll1 8/SM", in, o1, o2, n, sms * 8);
     run<LD_NA, ST_CS, 1, 2, 24>("1R2W +24 DFMA unroll1 one-shot", in, o1, o2, n, 0);
     run<LD_NA, ST_CS, 2, 2, 24>("1R2W +24 DFMA unroll2 one-shot", in, o1, o2, n, 0);
+    puts("--- sustained: 300 back-to-back launches (1R:2W +24 DFMA, unroll 1, one tile per block), avg per 50");
+    {
+        const uint32_t nvec = (uint32_t)(n / 4);
+        const int grid = (int)((nvec + 255u) / 256u);
+        cudaEvent_t ev[7];
+        for (auto& evt : ev) CK(cudaEventCreate(&evt));
+        CK(cudaEventRecord(ev[0]));
+        for (int b = 0; b < 6; ++b) {
+            for (int i = 0; i < 50; ++i) stream_kernel<LD_NA, ST_CS, 1, 2, 24><<<grid, 256>>>(in, o1, o2, nvec);
+            CK(cudaEventRecord(ev[b + 1]));
+        }
+        CK(cudaDeviceSynchronize());
+        for (int b = 0; b < 6; ++b) {
+            float ms;
+            CK(cudaEventElapsedTime(&ms, ev[b], ev[b + 1]));
+            printf("launches %3d..%3d: %8.1f GB/s\n", b * 50, b * 50 + 49, (double)n * 24.0 * 50 / (ms * 1e-3) / 1e9);
+        }
+    }
     return 0;
 }
