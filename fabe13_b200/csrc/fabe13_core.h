@@ -101,15 +101,25 @@ FABE13_HD double fabe13_from_bits(uint64_t u) {
 // 1. quadrant index, reference op sequence (fabe13/fabe13.c:568-571; same in :494-497, :426-429, :299-301)
 //    returns k as a double; *k_int receives k as an integer (valid for |k| < 2^51, i.e. far beyond the 2^45 cut)
 // ---------------------------------------------------------------------------------------------------------------
-FABE13_HD double fabe13_quadrant_index(double x, int64_t* k_int) {
+FABE13_HD double fabe13_quadrant_index(double x, double* biased_out) {
     const double p_hi = FABE13_MUL(x, FABE13_CF(k_hi));
     const double e1 = FABE13_FMA(x, FABE13_CF(k_hi), -p_hi);
     const double p_lo = FABE13_FMA(x, FABE13_CF(k_lo), e1);
     const double sum = FABE13_ADD(p_hi, p_lo);
     // rint() by the 1.5*2^52 bias: the biased sum carries k in its low mantissa bits (two's complement)
     const double biased = FABE13_ADD(sum, FABE13_CF(magic));
-    *k_int = (int64_t)(fabe13_bits(biased) - 0x4338000000000000ull);
+    *biased_out = biased;
     return FABE13_ADD(biased, FABE13_CF(neg_magic));
+}
+
+// k as an integer, and q = k mod 4 from the low word only (32-bit work on the device)
+FABE13_HD int64_t fabe13_k_from_biased(double biased) { return (int64_t)(fabe13_bits(biased) - 0x4338000000000000ull); }
+FABE13_HD uint32_t fabe13_q_from_biased(double biased) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(biased) & 3u;
+#else
+    return (uint32_t)fabe13_bits(biased) & 3u;
+#endif
 }
 
 // 2a. Cody-Waite with a correct three-word pi/2.  x - k*P1 is exact (a multiple of 2^-52 below 2), the two
@@ -286,7 +296,22 @@ FABE13_HD void fabe13_core(double r, double* s, double* c) {
 // 4. fix-up on bit patterns: rotate by q = k mod 4 (reference :586-596), then the tiny and special overrides
 //    (:597-600).  No FP64-pipe instructions: selects and XORs on the integer pipe.
 // ---------------------------------------------------------------------------------------------------------------
-FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, unsigned q, uint64_t* s_bits, uint64_t* c_bits) {
+// hi-word classification of |x|.  The tiny test uses the high word only: it also catches 2^-27 < |x| < 2^-27(1+2^-20),
+// where the polynomial path would return exactly (x, 1.0) as well (x^3/6 < ulp(x)/2 and x^2/2 < 2^-54), so the
+// result is the same bit for bit as with the reference's inclusive <= 2^-27 compare (fabe13.c:71, :567).
+FABE13_HD uint32_t fabe13_abs_hi(uint64_t x_bits) { return (uint32_t)(x_bits >> 32) & 0x7FFFFFFFu; }
+FABE13_HD bool fabe13_is_special(uint32_t ahi) { return ahi >= 0x7FF00000u; }                    // NaN, +-Inf
+FABE13_HD bool fabe13_is_tiny(uint32_t ahi) { return ahi <= FABE13_TINY_HI_WORD; }               // |x| <= 2^-27 (+sliver)
+FABE13_HD bool fabe13_is_huge(uint32_t ahi) { return (ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD); }
+// neither tiny, nor Payne-Hanek range, nor special: one subtract and one compare
+FABE13_HD bool fabe13_is_plain(uint32_t ahi) {
+    return (ahi - (FABE13_TINY_HI_WORD + 1u)) < (FABE13_PH_HI_WORD - (FABE13_TINY_HI_WORD + 1u));
+}
+
+// STASH_HUGE = true is the first pass of the array path: a lane in the Payne-Hanek range gets x itself in its sin
+// slot (the second pass picks it up from there), which costs nothing extra because it shares the override select.
+template <bool STASH_HUGE>
+FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, uint32_t q, uint64_t* s_bits, uint64_t* c_bits) {
     const uint64_t sb = fabe13_bits(sin_r);
     const uint64_t cb = fabe13_bits(cos_r);
     const bool swap = (q & 1u) != 0;
@@ -294,10 +319,10 @@ FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, unsigne
     uint64_t co = swap ? sb : cb;
     so ^= (uint64_t)(q & 2u) << 62;
     co ^= (uint64_t)((q + 1u) & 2u) << 62;
-    // overrides, merged into one select per output: tiny -> (x, 1); NaN/Inf -> (qNaN, qNaN)
-    const uint64_t ax = x_bits & FABE13_ABS_MASK;
-    const bool special = ax >= FABE13_INF_BITS;
-    const bool override_ = special || ax <= FABE13_TINY_BITS;
+    // overrides, merged into one select per output: tiny -> (x, 1); NaN/Inf -> (qNaN, qNaN); [stash -> (x, any)]
+    const uint32_t ahi = fabe13_abs_hi(x_bits);
+    const bool special = fabe13_is_special(ahi);
+    const bool override_ = STASH_HUGE ? !fabe13_is_plain(ahi) : (special || fabe13_is_tiny(ahi));
     const uint64_t alt_s = special ? FABE13_QNAN_BITS : x_bits;
     const uint64_t alt_c = special ? FABE13_QNAN_BITS : FABE13_ONE_BITS;
     so = override_ ? alt_s : so;
@@ -311,29 +336,30 @@ FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, unsigne
 template <int CORE>
 FABE13_HD void fabe13_sincos_one(uint64_t x_bits, const uint64_t* ph_table, uint64_t* s_bits, uint64_t* c_bits,
                                  int64_t* k_out) {
-    const uint64_t ax = x_bits & FABE13_ABS_MASK;
+    const uint32_t ahi = fabe13_abs_hi(x_bits);
     double r;
-    unsigned q;
+    uint32_t q;
     int64_t k;
-    if (ax >= FABE13_HUGE_BITS && ax < FABE13_INF_BITS) {
+    if (fabe13_is_huge(ahi)) {
         int qa;
-        r = fabe13_payne_hanek(ax, ph_table, &qa);
+        r = fabe13_payne_hanek(x_bits & FABE13_ABS_MASK, ph_table, &qa);
         if (x_bits >> 63) {  // odd symmetry: k(-x) = -k(x), r(-x) = -r(x)
             r = -r;
             qa = (4 - qa) & 3;
         }
-        q = (unsigned)qa;
+        q = (uint32_t)qa;
         k = qa;
     } else {
         const double x = fabe13_from_bits(x_bits);
-        const double kd = fabe13_quadrant_index(x, &k);
+        double biased;
+        const double kd = fabe13_quadrant_index(x, &biased);
         r = fabe13_cody_waite(x, kd);
-        q = (unsigned)k & 3u;
-        if (ax >= FABE13_INF_BITS) k = 0;
+        q = fabe13_q_from_biased(biased);
+        k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
     }
     double sr, cr;
     fabe13_core<CORE>(r, &sr, &cr);
-    fabe13_fixup(x_bits, sr, cr, q, s_bits, c_bits);
+    fabe13_fixup<false>(x_bits, sr, cr, q, s_bits, c_bits);
     *k_out = k;
 }
 

@@ -50,6 +50,7 @@ struct StreamArgs {
     uint32_t head;     // scalar elements before the vector body
     uint32_t nvec;     // vectors in the body
     uint32_t ntiles;   // tiles of kThreads*UNROLL vectors
+    uint32_t tiles_per_block;  // consecutive tiles one block takes per grid-stride step
     Worklist wl;
 };
 
@@ -88,22 +89,24 @@ __device__ __forceinline__ void store_stream<1>(void* p, const uint64_t (&b)[1])
     asm volatile("st.global.cs.b64 [%0], %1;" ::"l"(p), "l"(b[0]) : "memory");
 }
 
-// ---- one lane of the fast path.  Returns true if the lane belongs to the Payne-Hanek pass; in that case the
-//      sin slot carries x itself (the second pass reads it back from there, so in-place calls stay correct).
-template <int CORE>
+// 2^45 <= |v| < Inf: an argument parked in the sin array by the first pass (no sine has that magnitude)
+__device__ __forceinline__ bool is_stashed(uint64_t bits) { return fabe13_is_huge(fabe13_abs_hi(bits)); }
+
+// ---- one lane of the fast path.  Returns false for lanes that took an override (tiny, NaN/Inf, or Payne-Hanek
+//      range); a lane in the Payne-Hanek range leaves x itself in its sin slot (the second pass reads it back from
+//      there, so in-place calls stay correct).
+template <int CORE, bool WITH_K>
 __device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& cb, long long& k) {
-    const uint32_t ahi = (uint32_t)(xb >> 32) & 0x7FFFFFFFu;
-    const bool huge = (ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD);  // 2^45 <= |x| < Inf
     const double x = __longlong_as_double((long long)xb);
-    int64_t kk;
-    const double kd = fabe13_quadrant_index(x, &kk);
+    double biased;
+    const double kd = fabe13_quadrant_index(x, &biased);
     const double r = fabe13_cody_waite(x, kd);
     double sr, cr;
     fabe13_core<CORE>(r, &sr, &cr);
-    fabe13_fixup(xb, sr, cr, (unsigned)kk & 3u, &sb, &cb);
-    sb = huge ? xb : sb;
-    k = (ahi >= 0x7FF00000u) ? 0 : kk;
-    return huge;
+    fabe13_fixup<true>(xb, sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
+    const uint32_t ahi = fabe13_abs_hi(xb);
+    if (WITH_K) k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
+    return fabe13_is_plain(ahi);
 }
 
 // Append this warp's flagged elements (`mine` per lane, indices produced by `emit`) to the block's worklist segment:
@@ -132,59 +135,67 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
     double* so = a.sin_out + a.head;
     double* co = a.cos_out + a.head;
 
-    // grid-stride over tiles; the trip count is block-uniform, so the ballots below always see full warps
-    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
-        uint64_t xb[UNROLL][VEC];
-        bool live[UNROLL];
+    // grid-stride over chunks of tiles_per_block consecutive tiles; trip counts are block-uniform, so the ballots
+    // below always see full warps
+    for (uint32_t chunk = blockIdx.x; chunk * a.tiles_per_block < a.ntiles; chunk += gridDim.x) {
+        const uint32_t tile_end = min(a.ntiles, (chunk + 1) * a.tiles_per_block);
+        for (uint32_t tile = chunk * a.tiles_per_block; tile < tile_end; ++tile) {
+            const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
+            uint64_t xb[UNROLL][VEC];
+            bool live[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t v = v0 + u * kThreads;
-            live[u] = v < a.nvec;
-            if (live[u]) {
-                load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
-            } else {
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t v = v0 + u * kThreads;
+                live[u] = v < a.nvec;
+                if (live[u]) {
+                    load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) xb[u][j] = 0;
-            }
-        }
-        uint32_t n_huge = 0;
-        uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
-        long long kk[UNROLL][VEC];
-        bool huge[UNROLL][VEC];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                huge[u][j] = fast_lane<CORE>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);  // xb == 0 when !live: never huge
-                n_huge += huge[u][j] ? 1u : 0u;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            if (live[u]) {
-                const size_t e = (size_t)(v0 + u * kThreads) * VEC;
-                store_stream<VEC>(so + e, sb[u]);
-                store_stream<VEC>(co + e, cb[u]);
-                if (WITH_K) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
+                    for (int j = 0; j < VEC; ++j) xb[u][j] = 0x3FF0000000000000ull;  // 1.0: a plain lane
                 }
             }
-        }
-        if (__any_sync(0xFFFFFFFFu, n_huge != 0)) {  // rare: compact the Payne-Hanek lanes of this warp
-            worklist_push(n_huge, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
+            bool all_plain = true;
+            uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
+            long long kk[UNROLL][VEC];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (live[u]) {
+                    const size_t e = (size_t)(v0 + u * kThreads) * VEC;
+                    store_stream<VEC>(so + e, sb[u]);
+                    store_stream<VEC>(co + e, cb[u]);
+                    if (WITH_K) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
+                    }
+                }
+            }
+            if (__any_sync(0xFFFFFFFFu, !all_plain)) {  // rare: some lane is tiny, special or in the Payne-Hanek range
+                uint32_t n_huge = 0;
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        if (huge[u][j]) {
-                            if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
-                            ++slot;
-                        }
-                    }
+                    for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
                 }
-            });
+                if (__any_sync(0xFFFFFFFFu, n_huge != 0)) {  // compact the Payne-Hanek lanes of this warp
+                    worklist_push(n_huge, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
+#pragma unroll
+                        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) {
+                                if (is_stashed(xb[u][j])) {
+                                    if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
+                                    ++slot;
+                                }
+                            }
+                        }
+                    });
+                }
+            }
         }
     }
 
@@ -194,10 +205,11 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
         const uint32_t n_edge = a.head + (a.n - body_end);
         const bool on = lane < n_edge;
         const uint32_t idx = lane < a.head ? lane : body_end + (lane - a.head);
-        uint64_t xb = 0, sb, cb;
-        long long k;
+        uint64_t xb = 0x3FF0000000000000ull, sb, cb;
+        long long k = 0;
         if (on) xb = (uint64_t)__double_as_longlong(a.in[idx]);
-        const bool huge = fast_lane<CORE>(xb, sb, cb, k);
+        fast_lane<CORE, WITH_K>(xb, sb, cb, k);
+        const bool huge = is_stashed(xb);
         if (on) {
             a.sin_out[idx] = __longlong_as_double((long long)sb);
             a.cos_out[idx] = __longlong_as_double((long long)cb);
@@ -225,12 +237,6 @@ __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t
     a.sin_out[idx] = __longlong_as_double((long long)sb);
     a.cos_out[idx] = __longlong_as_double((long long)cb);
     if (a.k_out) a.k_out[idx] = k;
-}
-
-// 2^45 <= |v| < Inf: an argument parked in the sin array by the first pass (no sine has that magnitude)
-__device__ __forceinline__ bool is_stashed(uint64_t bits) {
-    const uint32_t ahi = (uint32_t)(bits >> 32) & 0x7FFFFFFFu;
-    return (ahi - FABE13_PH_HI_WORD) < (0x7FF00000u - FABE13_PH_HI_WORD);
 }
 
 __device__ __forceinline__ void stage_table(uint64_t* table) {
@@ -399,9 +405,10 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     cudaError_t err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
     if (err != cudaSuccess) return err;
 
-    // blocks_per_sm == 0: one tile per block (the block scheduler walks the array in address order);
-    // otherwise a persistent grid of SMs*blocks_per_sm blocks strides over the tiles.
-    long long grid = a.ntiles;
+    // blocks_per_sm == 0: one chunk of tiles_per_block tiles per block (the block scheduler walks the array in
+    // address order); otherwise a persistent grid of SMs*blocks_per_sm blocks strides over the chunks.
+    a.tiles_per_block = (uint32_t)(t.tiles_per_block > 0 ? t.tiles_per_block : 1);
+    long long grid = ((long long)a.ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
     if (t.blocks_per_sm > 0 && grid > (long long)dev.sm_count * t.blocks_per_sm) grid = (long long)dev.sm_count * t.blocks_per_sm;
     if (grid < 1) grid = 1;
     err = d_k ? launch_stream_vec<CORE, true>(a, vec, unroll, (int)grid, stream)

@@ -40,7 +40,7 @@ def gpu_sincos(fabe13, cuda, x):
 
 @pytest.fixture(autouse=True)
 def _defaults(fabe13):
-    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "second_pass_blocks_per_sm", "small_n", "worklist_shift")}
+    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift")}
     yield
     for k, v in saved.items():
         fabe13.set_option(k, v)
@@ -168,9 +168,10 @@ def test_c3_1e9_properties(fabe13, cuda, oracle):
 # ---------------------------------------------------------------------------------------------------------------
 # C4: extreme-range mix -- the Payne-Hanek worklist (sparse), its overflow rescan (dense) and the inline kernel
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("core", [0, 1])
-def test_c4_dense_loguniform(fabe13, cuda, oracle, core):
+@pytest.mark.parametrize("core,small_n", [(0, 0), (1, 0), (0, 1 << 30)])
+def test_c4_dense_loguniform(fabe13, cuda, oracle, core, small_n):
     fabe13.set_option("core", core)
+    fabe13.set_option("small_n", small_n)  # 0: streaming kernel + second pass; 2^30: the inline kernel
     n = 4_000_000
     x = oracle.fill_loguniform(n, SEED_C4)
     assert (np.abs(x) >= HUGE).mean() > 0.9
@@ -182,6 +183,7 @@ def test_c4_dense_loguniform(fabe13, cuda, oracle, core):
 
 
 def test_c4_sparse_mix_uses_the_worklist(fabe13, cuda, oracle):
+    fabe13.set_option("small_n", 0)
     n = 8_000_000
     x = oracle.fill_uniform(n, SEED_C2, -1e4, 1e4)
     h = oracle.fill_loguniform(n, SEED_C4)
@@ -202,6 +204,7 @@ def test_worklist_capacity_and_overflow(fabe13, cuda, oracle, shift):
     """worklist_shift=20 leaves room for only 1024 entries: everything else must come out of the rescan pass;
     shift=0 holds every lane.  Results are identical either way."""
     fabe13.set_option("worklist_shift", shift)
+    fabe13.set_option("small_n", 0)
     n = 3_000_001
     x = oracle.fill_uniform(n, 9, -1e6, 1e6)
     h = oracle.fill_loguniform(n, 10)
@@ -216,6 +219,7 @@ def test_caller_provided_workspace(fabe13, cuda, oracle):
     import torch
 
     lib = fabe13._lib.load()
+    fabe13.set_option("small_n", 0)
     n = 2_000_000
     x = oracle.fill_uniform(n, 19, -1e5, 1e5)
     x[::1000] = oracle.fill_loguniform(n // 1000, 20)
@@ -246,7 +250,7 @@ def edge_pattern(golden, n):
     return np.tile(pool, reps)[:n].copy()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 10, 31, 32, 33, 100, 1000, 10_000, 100_000, 262_143, 262_144, 262_145, 1_000_000])
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 31, 32, 33, 100, 1000, 10_000, 100_000, 1_000_000, 4_194_303, 4_194_304, 4_194_305])
 def test_c5_edge_sweep(fabe13, cuda, oracle, golden, n):
     x = edge_pattern(golden, n)
     s, c, k = gpu_sincos_k(fabe13, cuda, x)
@@ -295,9 +299,11 @@ def test_misaligned_and_incongruent_pointers(fabe13, cuda, oracle, off_in, off_s
         assert np.all(out == 7.0)
 
 
-def test_in_place(fabe13, cuda, oracle):
+@pytest.mark.parametrize("small_n", [0, 1 << 30])
+def test_in_place(fabe13, cuda, oracle, small_n):
     import torch
 
+    fabe13.set_option("small_n", small_n)
     n = 1_000_003
     x = oracle.fill_uniform(n, 56, -1e6, 1e6)
     x[::500] = oracle.fill_loguniform((n + 499) // 500, 57)
@@ -309,9 +315,10 @@ def test_in_place(fabe13, cuda, oracle):
     assert np.array_equal(bits(xt.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
 
 
-@pytest.mark.parametrize("blocks_per_sm", [0, 1, 3, 8])
-def test_grid_size_does_not_change_results(fabe13, cuda, oracle, blocks_per_sm):
+@pytest.mark.parametrize("blocks_per_sm,tiles_per_block", [(0, 1), (0, 4), (0, 1000), (1, 1), (3, 2), (8, 1)])
+def test_grid_shape_does_not_change_results(fabe13, cuda, oracle, blocks_per_sm, tiles_per_block):
     fabe13.set_option("blocks_per_sm", blocks_per_sm)
+    fabe13.set_option("tiles_per_block", tiles_per_block)
     x = oracle.fill_uniform(5_000_011, 58, -1e4, 1e4)
     s, c = gpu_sincos(fabe13, cuda, x)
     hs, hc, _ = fabe13.host_core(x, 0)
@@ -397,6 +404,7 @@ def test_streams_and_concurrency(fabe13, cuda, oracle):
     """The device entry is stream-ordered: two streams, interleaved launches, no host synchronisation in between."""
     import torch
 
+    fabe13.set_option("small_n", 1_000_000)
     x1 = torch.from_numpy(oracle.fill_uniform(2_000_000, 90, -1e4, 1e4)).to(cuda)
     x2 = torch.from_numpy(oracle.fill_loguniform(2_000_000, 91)).to(cuda)
     st1, st2 = torch.cuda.Stream(), torch.cuda.Stream()
@@ -421,6 +429,7 @@ def test_multi_entry_single_device(fabe13, cuda, oracle):
     import torch
 
     lib = fabe13._lib.load()
+    fabe13.set_option("small_n", 100_000)
     n = 1_000_001
     x = oracle.fill_uniform(n, 95, -1e4, 1e4)
     xt = torch.from_numpy(x).to(cuda)

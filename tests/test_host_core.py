@@ -75,3 +75,19 @@ def test_pythagorean_identity(fabe13, oracle):
     for core in CORES:
         s, c, _ = fabe13.host_core(x, core)
         assert np.abs(s * s + c * c - 1.0).max() <= 8e-16
+
+
+def test_tiny_threshold_high_word_test_is_equivalent(fabe13, oracle):
+    """The device classifies |x| <= 2^-27 by the high word only, which also sweeps in 2^-27 < |x| < 2^-27(1+2^-20).
+    There the polynomial path returns exactly (x, 1.0) too, so outputs must still equal the reference's bit for bit
+    on both sides of the high-word boundary."""
+    base = np.uint64(0x3E40000000000000)
+    xs = np.concatenate([
+        (base + np.arange(0, 1 << 20, 7, dtype=np.uint64)).view(np.float64),                           # in the sliver
+        (base + np.uint64((1 << 32) - 1) - np.arange(0, 50_000, dtype=np.uint64)).view(np.float64),    # its top end
+        (base + np.uint64(1 << 32) + np.arange(0, 50_000, dtype=np.uint64)).view(np.float64),          # just above it
+    ])
+    xs = np.concatenate([xs, -xs])
+    s, c, _ = fabe13.host_core(xs, 0)
+    rs, rc, _ = oracle.sincos(xs)
+    assert np.array_equal(bits(s), bits(rs)) and np.array_equal(bits(c), bits(rc))

@@ -47,17 +47,20 @@ def main():
     fb.fill_uniform_device(x, 0xFABE1303, -1e4, 1e4)
     for core in (0, 1):
         fb.set_option("core", core)
-        for unroll in (1, 2, 4):
+        for unroll in (1, 2):
             fb.set_option("unroll", unroll)
-            for bps in (0, 2, 3, 4, 6, 8, 16, 32):
+            for bps in (0, 4, 32):
                 fb.set_option("blocks_per_sm", bps)
-                avg, best = time_steps(x, s, c)
-                report(f"c3 n={n} core={core} unroll={unroll} blocks_per_sm={bps}", n, avg, best)
+                for tpb in ((1, 2, 4, 8, 16) if bps == 0 else (1,)):
+                    fb.set_option("tiles_per_block", tpb)
+                    avg, best = time_steps(x, s, c)
+                    report(f"c3 n={n} core={core} unroll={unroll} blocks_per_sm={bps} tiles_per_block={tpb}", n, avg, best)
+    fb.set_option("tiles_per_block", 1)
     fb.set_option("core", 0)
     fb.set_option("unroll", 1)
     fb.set_option("blocks_per_sm", 0)
     # other sizes / workloads with the defaults
-    for m in (10, 1000, 16384, 100_000, 262_143, 262_144, 1_000_000, 10_000_000, 100_000_000):
+    for m in (10, 1000, 100_000, 1_000_000, 4_194_303, 4_194_304, 10_000_000, 100_000_000):
         avg, best = time_steps(x[:m], s[:m], c[:m], steps=20)
         print(f"uniform n={m:>11d}: avg {avg * 1e3:9.1f} us  best {best * 1e3:9.1f} us  {m / best / 1e6:9.3f} Gelem/s", flush=True)
     m = 100_000_000
