@@ -48,6 +48,7 @@ struct Config {
     std::atomic<long long> chunk_elems{(long long)1 << 22};
     std::atomic<long long> host_devices{1};
     std::atomic<long long> stage_threads{4};
+    std::atomic<long long> zero_copy_max{32768};
 };
 
 Config g_cfg;
@@ -73,6 +74,7 @@ const OptionDesc kOptions[] = {
     {"chunk_elems", "FABE13_CUDA_CHUNK_ELEMS", &Config::chunk_elems, 1024, (long long)1 << 28},
     {"host_devices", "FABE13_CUDA_HOST_DEVICES", &Config::host_devices, 1, kMaxDevices},
     {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 1, kSlots},
+    {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 24},
 };
 
 void load_env() {
@@ -141,6 +143,9 @@ struct DeviceState {
     char name[256] = {0};
     // host path
     std::mutex pipe_mu;
+    cudaStream_t small_stream = nullptr;  // small host calls: one kernel reading/writing pinned host memory directly
+    double* small_stage = nullptr;        // pinned, 3 * small_cap doubles (in | sin | cos), for pageable callers
+    size_t small_cap = 0;
     size_t chunk_cap = 0;
     size_t ws_bytes = 0;
     bool staging = false;
@@ -299,6 +304,50 @@ int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, 
     return 0;
 }
 
+// Small host-resident arrays: launch latency dominates, so skip the copy engines.  One kernel reads the pinned
+// host buffer over PCIe and writes both results straight back (zero-copy through the unified address space).
+// Pageable callers are bounced through a small pinned staging block.  Returns -1 if this route is not available
+// (memory registered without a device mapping), in which case the caller takes the copy pipeline.
+int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned,
+               const LaunchTuning& t, int core) {
+    if (!s.small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&s.small_stream, cudaStreamNonBlocking));
+    const double* src = in;
+    double *dst_s = sin_out, *dst_c = cos_out;
+    if (!pinned) {
+        if (s.small_cap < n) {
+            if (s.small_stage) cudaFreeHost(s.small_stage);
+            s.small_stage = nullptr;
+            s.small_cap = 0;
+            const size_t cap = (size_t)g_cfg.zero_copy_max.load() > n ? (size_t)g_cfg.zero_copy_max.load() : n;
+            FABE13_TRY(cudaHostAlloc(&s.small_stage, 3 * cap * sizeof(double), cudaHostAllocDefault));
+            s.small_cap = cap;
+        }
+        memcpy(s.small_stage, in, n * sizeof(double));
+        src = s.small_stage;
+        dst_s = s.small_stage + s.small_cap;
+        dst_c = s.small_stage + 2 * s.small_cap;
+    }
+    void *d_in, *d_s, *d_c;
+    if (cudaHostGetDevicePointer(&d_in, (void*)src, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_s, dst_s, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(&d_c, dst_c, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    int launches = 0;
+    LaunchTuning ti = t;
+    ti.small_n = 1 << 30;  // always the single inline kernel here
+    cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, core, ti, s.info, nullptr,
+                                          s.small_stream, &launches);
+    g_launches.fetch_add((unsigned long long)launches);
+    if (e != cudaSuccess) return record(e, "launch_sincos(zero-copy)");
+    FABE13_TRY(cudaStreamSynchronize(s.small_stream));
+    if (!pinned) {
+        memcpy(sin_out, dst_s, n * sizeof(double));
+        memcpy(cos_out, dst_c, n * sizeof(double));
+    }
+    return 0;
+}
+
 // One device, one contiguous slice.  Caller has made `dev` current.
 int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned) {
     DeviceState* ds;
@@ -306,6 +355,10 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     std::lock_guard<std::mutex> lk(ds->pipe_mu);
     const LaunchTuning t = current_tuning();
     const int core = (int)g_cfg.core.load();
+    if (n <= (size_t)g_cfg.zero_copy_max.load()) {
+        const int rc = host_small(*ds, in, sin_out, cos_out, n, pinned, t, core);
+        if (rc >= 0) return rc;
+    }
     const size_t chunk = pick_chunk(n);
     if (int rc = ensure_slots(*ds, chunk, !pinned, t)) return rc;
     const size_t nchunks = (n + chunk - 1) / chunk;

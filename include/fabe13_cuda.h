@@ -45,7 +45,8 @@ int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in,
 /* Host-pointer entry with a size_t length and an error return; fabe13_sincos() forwards here.
  * Pinned host memory (cudaHostAlloc / cudaHostRegister / fabe13_cuda_host_alloc) is copied directly by the copy
  * engines, H2D and D2H overlapped with the kernel chunk by chunk; pageable memory goes through pinned staging
- * buffers filled by worker threads.  With option "host_devices" > 1 the array is split into contiguous slices,
+ * buffers filled by worker threads.  Arrays of at most "zero_copy_max" elements skip the copy engines: one kernel
+ * reads the pinned host buffer and writes the results back directly over PCIe.  With option "host_devices" > 1 the array is split into contiguous slices,
  * one per GPU. */
 int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n);
 
@@ -58,7 +59,7 @@ void fabe13_cuda_host_free(void* p);
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
 
 /* Options: "core" (0/1), "unroll" (1/2/4), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
- * per SM), "second_pass_blocks_per_sm", "small_n", "worklist_shift", "chunk_elems", "host_devices", "stage_threads".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
+ * per SM), "second_pass_blocks_per_sm", "small_n", "worklist_shift", "chunk_elems", "host_devices", "stage_threads", "zero_copy_max", "tiles_per_block".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);
 int fabe13_cuda_get_option(const char* key, long long* value);
