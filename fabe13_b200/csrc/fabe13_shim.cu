@@ -29,7 +29,7 @@ using fabe13::DeviceInfo;
 using fabe13::LaunchTuning;
 
 constexpr int kMaxDevices = 64;
-constexpr int kSlots = 4;                                  // pipeline depth of the host path
+constexpr int kSlots = 8;                                  // pipeline depth of the host path / max staging workers
 constexpr size_t kLaunchMaxElems = (size_t)1 << 30;        // per launch sequence; keeps 32-bit indices and alignment
 
 const uint64_t h_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
@@ -47,7 +47,7 @@ struct Config {
     std::atomic<long long> worklist_shift{3};
     std::atomic<long long> chunk_elems{(long long)1 << 22};
     std::atomic<long long> host_devices{1};
-    std::atomic<long long> stage_threads{4};
+    std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, hardware threads / 2)
     std::atomic<long long> zero_copy_max{32768};
 };
 
@@ -73,7 +73,7 @@ const OptionDesc kOptions[] = {
     {"worklist_shift", "FABE13_CUDA_WORKLIST_SHIFT", &Config::worklist_shift, 0, 20},
     {"chunk_elems", "FABE13_CUDA_CHUNK_ELEMS", &Config::chunk_elems, 1024, (long long)1 << 28},
     {"host_devices", "FABE13_CUDA_HOST_DEVICES", &Config::host_devices, 1, kMaxDevices},
-    {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 1, kSlots},
+    {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 0, kSlots},
     {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 24},
 };
 
@@ -148,7 +148,7 @@ struct DeviceState {
     size_t small_cap = 0;
     size_t chunk_cap = 0;
     size_t ws_bytes = 0;
-    bool staging = false;
+    size_t stage_cap = 0;  // elements per pinned staging buffer (pageable callers only)
     Slot slots[kSlots];
 };
 
@@ -253,7 +253,7 @@ void free_slots(DeviceState& s) {
         sl.h_in = sl.h_sin = sl.h_cos = nullptr;
     }
     s.chunk_cap = 0;
-    s.staging = false;
+    s.stage_cap = 0;
 }
 
 // (re)size the slots of the current device for `chunk` elements; pinned staging only if asked for
@@ -270,13 +270,20 @@ int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning&
         }
         s.chunk_cap = chunk;
     }
-    if (staging && !s.staging) {
+    if (staging && s.stage_cap < chunk) {
         for (Slot& sl : s.slots) {
-            FABE13_TRY(cudaHostAlloc(&sl.h_in, s.chunk_cap * sizeof(double), cudaHostAllocDefault));
-            FABE13_TRY(cudaHostAlloc(&sl.h_sin, s.chunk_cap * sizeof(double), cudaHostAllocDefault));
-            FABE13_TRY(cudaHostAlloc(&sl.h_cos, s.chunk_cap * sizeof(double), cudaHostAllocDefault));
+            if (sl.h_in) cudaFreeHost(sl.h_in);
+            if (sl.h_sin) cudaFreeHost(sl.h_sin);
+            if (sl.h_cos) cudaFreeHost(sl.h_cos);
+            sl.h_in = sl.h_sin = sl.h_cos = nullptr;
         }
-        s.staging = true;
+        s.stage_cap = 0;
+        for (Slot& sl : s.slots) {
+            FABE13_TRY(cudaHostAlloc(&sl.h_in, chunk * sizeof(double), cudaHostAllocDefault));
+            FABE13_TRY(cudaHostAlloc(&sl.h_sin, chunk * sizeof(double), cudaHostAllocDefault));
+            FABE13_TRY(cudaHostAlloc(&sl.h_cos, chunk * sizeof(double), cudaHostAllocDefault));
+        }
+        s.stage_cap = chunk;
     }
     return 0;
 }
@@ -359,7 +366,8 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
         const int rc = host_small(*ds, in, sin_out, cos_out, n, pinned, t, core);
         if (rc >= 0) return rc;
     }
-    const size_t chunk = pick_chunk(n);
+    size_t chunk = pick_chunk(n);
+    if (!pinned && chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;  // staged: 8 MB pieces, one per worker in flight
     if (int rc = ensure_slots(*ds, chunk, !pinned, t)) return rc;
     const size_t nchunks = (n + chunk - 1) / chunk;
 
@@ -378,6 +386,10 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     // pageable memory: worker w owns slot w and the chunks i = w (mod workers); it copies the chunk into pinned
     // staging, runs it, waits, and copies the results out.  Workers overlap each other's stages.
     int workers = (int)g_cfg.stage_threads.load();
+    if (workers <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        workers = (int)(hw / 2 > (unsigned)kSlots ? (unsigned)kSlots : (hw / 2 ? hw / 2 : 1));
+    }
     if ((size_t)workers > nchunks) workers = (int)nchunks;
     std::atomic<int> rc_all{0};
     auto work = [&](int w) {
