@@ -126,6 +126,7 @@ int record(cudaError_t e, const char* where) {
 // ---------------------------------------------------------------------------------------------------------------
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
     double* d_in = nullptr;   // chunk_cap elements each
     double* d_sin = nullptr;
     double* d_cos = nullptr;
@@ -263,6 +264,7 @@ int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning&
         s.ws_bytes = fabe13::workspace_bytes(chunk, t);
         for (Slot& sl : s.slots) {
             if (!sl.stream) FABE13_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            if (!sl.done) FABE13_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventBlockingSync | cudaEventDisableTiming));
             FABE13_TRY(cudaMalloc(&sl.d_in, chunk * sizeof(double)));
             FABE13_TRY(cudaMalloc(&sl.d_sin, chunk * sizeof(double)));
             FABE13_TRY(cudaMalloc(&sl.d_cos, chunk * sizeof(double)));
@@ -379,7 +381,13 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             if (int rc = enqueue_chunk(*ds, ds->slots[i % kSlots], in + off, sin_out + off, cos_out + off, m, t, core))
                 return rc;
         }
-        for (Slot& sl : ds->slots) FABE13_TRY(cudaStreamSynchronize(sl.stream));
+        if (n >= ((size_t)1 << 22)) {
+            // large transfers: sleep on blocking events rather than spin (the wait is milliseconds long)
+            for (Slot& sl : ds->slots) FABE13_TRY(cudaEventRecord(sl.done, sl.stream));
+            for (Slot& sl : ds->slots) FABE13_TRY(cudaEventSynchronize(sl.done));
+        } else {
+            for (Slot& sl : ds->slots) FABE13_TRY(cudaStreamSynchronize(sl.stream));
+        }
         return 0;
     }
 
@@ -404,8 +412,9 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             memcpy(sl.h_in, in + off, m * sizeof(double));
             int rc = enqueue_chunk(*ds, sl, sl.h_in, sl.h_sin, sl.h_cos, m, t, core);
             if (rc == 0) {
-                cudaError_t e = cudaStreamSynchronize(sl.stream);
-                if (e != cudaSuccess) rc = record(e, "cudaStreamSynchronize(worker)");
+                cudaError_t e = cudaEventRecord(sl.done, sl.stream);
+                if (e == cudaSuccess) e = cudaEventSynchronize(sl.done);  // blocking event: the worker sleeps
+                if (e != cudaSuccess) rc = record(e, "cudaEventSynchronize(worker)");
             }
             if (rc != 0) {
                 rc_all.store(rc);
