@@ -91,3 +91,23 @@ def test_tiny_threshold_high_word_test_is_equivalent(fabe13, oracle):
     s, c, _ = fabe13.host_core(xs, 0)
     rs, rc, _ = oracle.sincos(xs)
     assert np.array_equal(bits(s), bits(rs)) and np.array_equal(bits(c), bits(rc))
+
+
+def test_against_mpmath_truth(fabe13, oracle):
+    """Independent truth (mpmath, 1200-bit pi) rather than glibc, on inputs chosen to hurt: huge magnitudes, the
+    double closest to a multiple of pi/2 (6381956970095103 * 2^797), both ends of the Payne-Hanek threshold."""
+    import mpmath as mp
+
+    mp.mp.prec = 1400
+    xs = np.concatenate([
+        np.array([1e22, -1e22, 1.7976931348623157e308, 2.0 ** 1023, 6381956970095103.0 * 2.0 ** 797, 2.0 ** 45,
+                  np.nextafter(2.0 ** 45, 0), 3.0e13, 1e15, 1e16, 1e100, 5e-324, 1e-300, 0.7853981633974483]),
+        oracle.fill_loguniform(150, 1234),
+        oracle.fill_uniform(150, 1235, -1e6, 1e6),
+    ])
+    for core, tol in ((0, 1.2e-16), (1, 4.5e-16)):
+        s, c, _ = fabe13.host_core(xs, core)
+        for x, si, ci in zip(xs, s, c):
+            xm = mp.mpf(float(x))
+            assert abs(mp.mpf(float(si)) - mp.sin(xm)) <= tol, (x, si)
+            assert abs(mp.mpf(float(ci)) - mp.cos(xm)) <= tol, (x, ci)
