@@ -9,6 +9,7 @@ from .api import (  # noqa: F401
     CORE_PSI,
     PinnedArray,
     cos,
+    cos_array,
     cot,
     fill_loguniform_device,
     fill_uniform_device,
@@ -19,6 +20,7 @@ from .api import (  # noqa: F401
     shard_bounds,
     simd_width,
     sin,
+    sin_array,
     sinc,
     sincos,
     sincos_k,

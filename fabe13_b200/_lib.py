@@ -34,6 +34,10 @@ def signatures():
         # fabe13_cuda.h
         "fabe13_sincos_device": (c.c_int, [_vp, _vp, _vp, c.c_size_t, _vp]),
         "fabe13_sincos_device_k": (c.c_int, [_vp, _vp, _vp, _vp, c.c_size_t, _vp]),
+        "fabe13_sin_device": (c.c_int, [_vp, _vp, c.c_size_t, _vp]),
+        "fabe13_cos_device": (c.c_int, [_vp, _vp, c.c_size_t, _vp]),
+        "fabe13_sin_host": (c.c_int, [_vp, _vp, c.c_size_t]),
+        "fabe13_cos_host": (c.c_int, [_vp, _vp, c.c_size_t]),
         "fabe13_sincos_workspace_bytes": (c.c_size_t, [c.c_size_t]),
         "fabe13_sincos_device_ws": (c.c_int, [_vp, _vp, _vp, c.c_size_t, _vp, c.c_size_t, _vp]),
         "fabe13_sincos_multi": (c.c_int, [c.c_int, _vp, _vp, _vp, _vp, _vp]),

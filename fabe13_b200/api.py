@@ -66,6 +66,37 @@ def sincos(x, out_sin=None, out_cos=None, stream=None):
     return s, c
 
 
+def _single(x, out, dev_fn, host_fn, what):
+    lib = _lib.load()
+    _check_f64(x, "x")
+    if _is_torch(x):
+        import torch
+
+        o = torch.empty_like(x) if out is None else out
+        _check_f64(o, "out")
+        if x.is_cuda:
+            with torch.cuda.device(x.device):
+                rc = getattr(lib, dev_fn)(x.data_ptr(), o.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = getattr(lib, host_fn)(x.data_ptr(), o.data_ptr(), x.numel())
+        _lib.check(rc, what)
+        return o
+    o = np.empty_like(x) if out is None else out
+    _check_f64(o, "out")
+    _lib.check(getattr(lib, host_fn)(x.ctypes.data, o.ctypes.data, x.size), what)
+    return o
+
+
+def sin_array(x, out=None):
+    """sin(x) element-wise (array form of fabe13_sin): CUDA tensor -> fabe13_sin_device, host array -> fabe13_sin_host."""
+    return _single(x, out, "fabe13_sin_device", "fabe13_sin_host", "fabe13_sin")
+
+
+def cos_array(x, out=None):
+    """cos(x) element-wise (array form of fabe13_cos)."""
+    return _single(x, out, "fabe13_cos_device", "fabe13_cos_host", "fabe13_cos")
+
+
 def sincos_k(x):
     """(sin, cos, k) for a torch CUDA float64 tensor; k is the reference's quadrant index (test hook)."""
     import torch

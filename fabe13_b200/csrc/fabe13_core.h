@@ -308,9 +308,13 @@ FABE13_HD bool fabe13_is_plain(uint32_t ahi) {
     return (ahi - (FABE13_TINY_HI_WORD + 1u)) < (FABE13_PH_HI_WORD - (FABE13_TINY_HI_WORD + 1u));
 }
 
-// STASH_HUGE = true is the first pass of the array path: a lane in the Payne-Hanek range gets x itself in its sin
-// slot (the second pass picks it up from there), which costs nothing extra because it shares the override select.
-template <bool STASH_HUGE>
+// STASH selects what a lane in the Payne-Hanek range leaves behind in the first pass of the array path: x itself in
+// its sin slot (FABE13_STASH_SIN; free, it shares the override select) or in its cos slot (FABE13_STASH_COS, used
+// when only cosines are produced).  The second pass picks the argument up from there.  FABE13_STASH_NONE is the
+// complete fix-up used wherever the reduction already handled every range.
+enum { FABE13_STASH_NONE = 0, FABE13_STASH_SIN = 1, FABE13_STASH_COS = 2 };
+
+template <int STASH>
 FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, uint32_t q, uint64_t* s_bits, uint64_t* c_bits) {
     const uint64_t sb = fabe13_bits(sin_r);
     const uint64_t cb = fabe13_bits(cos_r);
@@ -319,12 +323,13 @@ FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, uint32_
     uint64_t co = swap ? sb : cb;
     so ^= (uint64_t)(q & 2u) << 62;
     co ^= (uint64_t)((q + 1u) & 2u) << 62;
-    // overrides, merged into one select per output: tiny -> (x, 1); NaN/Inf -> (qNaN, qNaN); [stash -> (x, any)]
+    // overrides, merged into one select per output: tiny -> (x, 1); NaN/Inf -> (qNaN, qNaN); [stash -> x]
     const uint32_t ahi = fabe13_abs_hi(x_bits);
     const bool special = fabe13_is_special(ahi);
-    const bool override_ = STASH_HUGE ? !fabe13_is_plain(ahi) : (special || fabe13_is_tiny(ahi));
+    const bool override_ = (STASH != FABE13_STASH_NONE) ? !fabe13_is_plain(ahi) : (special || fabe13_is_tiny(ahi));
     const uint64_t alt_s = special ? FABE13_QNAN_BITS : x_bits;
-    const uint64_t alt_c = special ? FABE13_QNAN_BITS : FABE13_ONE_BITS;
+    uint64_t alt_c = special ? FABE13_QNAN_BITS : FABE13_ONE_BITS;
+    if (STASH == FABE13_STASH_COS) alt_c = fabe13_is_huge(ahi) ? x_bits : alt_c;
     so = override_ ? alt_s : so;
     co = override_ ? alt_c : co;
     *s_bits = so;
@@ -359,7 +364,7 @@ FABE13_HD void fabe13_sincos_one(uint64_t x_bits, const uint64_t* ph_table, uint
     }
     double sr, cr;
     fabe13_core<CORE>(r, &sr, &cr);
-    fabe13_fixup<false>(x_bits, sr, cr, q, s_bits, c_bits);
+    fabe13_fixup<FABE13_STASH_NONE>(x_bits, sr, cr, q, s_bits, c_bits);
     *k_out = k;
 }
 

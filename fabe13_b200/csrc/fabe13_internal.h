@@ -13,7 +13,7 @@ struct LaunchTuning {
     int blocks_per_sm;  // 0 = one tile per block (default); k > 0 = persistent grid of SMs * k blocks
     int tiles_per_block;  // consecutive tiles per block per grid-stride step
     int second_pass_blocks_per_sm;  // grid of the Payne-Hanek second pass
-    int unroll;         // 256-bit vectors in flight per thread: 1, 2 or 4
+    int unroll;         // 256-bit vectors in flight per thread: 1 or 2
     int small_n;        // n below this runs the single inline kernel (no worklist, one launch)
     int worklist_shift; // worklist capacity = n >> worklist_shift entries (0 = one entry per element)
 };
@@ -27,7 +27,8 @@ struct DeviceInfo {
 size_t workspace_bytes(size_t n, const LaunchTuning& t);
 
 // Enqueue the sincos path for n <= 2^31 elements on `stream`.  `workspace` must hold workspace_bytes(n) bytes
-// (it is zero-initialised here, on the stream).  d_k may be null.  Returns the number of kernels launched via
+// (it is zero-initialised here, on the stream).  d_k may be null.  One of d_sin / d_cos may be null: then only the
+// other output is produced (16 B/element instead of 24).  Returns the number of kernels launched via
 // *launches.  Every pointer is a device pointer on the current device.
 cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int core,
                           const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,

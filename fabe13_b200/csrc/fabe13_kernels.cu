@@ -41,10 +41,13 @@ struct Worklist {
     uint32_t seg_cap;
 };
 
+// which outputs a launch produces: both (the reference's fabe13_sincos), or one of them (16 B/element)
+enum { OUT_BOTH = 0, OUT_SIN = 1, OUT_COS = 2 };
+
 struct StreamArgs {
     const double* in;
-    double* sin_out;
-    double* cos_out;
+    double* sin_out;   // null when only cosines are produced
+    double* cos_out;   // null when only sines are produced
     long long* k_out;  // null unless WITH_K
     uint32_t n;        // elements in this launch (<= 2^31)
     uint32_t head;     // scalar elements before the vector body
@@ -95,7 +98,7 @@ __device__ __forceinline__ bool is_stashed(uint64_t bits) { return fabe13_is_hug
 // ---- one lane of the fast path.  Returns false for lanes that took an override (tiny, NaN/Inf, or Payne-Hanek
 //      range); a lane in the Payne-Hanek range leaves x itself in its sin slot (the second pass reads it back from
 //      there, so in-place calls stay correct).
-template <int CORE, bool WITH_K>
+template <int CORE, bool WITH_K, int OUT>
 __device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& cb, long long& k) {
     const double x = __longlong_as_double((long long)xb);
     double biased;
@@ -103,7 +106,7 @@ __device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& c
     const double r = fabe13_cody_waite(x, kd);
     double sr, cr;
     fabe13_core<CORE>(r, &sr, &cr);
-    fabe13_fixup<true>(xb, sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
+    fabe13_fixup<(OUT == OUT_COS) ? FABE13_STASH_COS : FABE13_STASH_SIN>(xb, sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
     const uint32_t ahi = fabe13_abs_hi(xb);
     if (WITH_K) k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
     return fabe13_is_plain(ahi);
@@ -128,12 +131,12 @@ __device__ __forceinline__ void worklist_push(uint32_t mine, const Worklist& wl,
     emit(wl.entries + (size_t)seg * wl.seg_cap, base + incl - mine);
 }
 
-template <int CORE, int VEC, int UNROLL, bool WITH_K>
+template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
 __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const double* in = a.in + a.head;
-    double* so = a.sin_out + a.head;
-    double* co = a.cos_out + a.head;
+    double* so = (OUT != OUT_COS) ? a.sin_out + a.head : nullptr;
+    double* co = (OUT != OUT_SIN) ? a.cos_out + a.head : nullptr;
 
     // grid-stride over chunks of tiles_per_block consecutive tiles; trip counts are block-uniform, so the ballots
     // below always see full warps
@@ -160,14 +163,14 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+                for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 if (live[u]) {
                     const size_t e = (size_t)(v0 + u * kThreads) * VEC;
-                    store_stream<VEC>(so + e, sb[u]);
-                    store_stream<VEC>(co + e, cb[u]);
+                    if (OUT != OUT_COS) store_stream<VEC>(so + e, sb[u]);
+                    if (OUT != OUT_SIN) store_stream<VEC>(co + e, cb[u]);
                     if (WITH_K) {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
@@ -208,11 +211,11 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
         uint64_t xb = 0x3FF0000000000000ull, sb, cb;
         long long k = 0;
         if (on) xb = (uint64_t)__double_as_longlong(a.in[idx]);
-        fast_lane<CORE, WITH_K>(xb, sb, cb, k);
+        fast_lane<CORE, WITH_K, OUT>(xb, sb, cb, k);
         const bool huge = is_stashed(xb);
         if (on) {
-            a.sin_out[idx] = __longlong_as_double((long long)sb);
-            a.cos_out[idx] = __longlong_as_double((long long)cb);
+            if (OUT != OUT_COS) a.sin_out[idx] = __longlong_as_double((long long)sb);
+            if (OUT != OUT_SIN) a.cos_out[idx] = __longlong_as_double((long long)cb);
             if (WITH_K) a.k_out[idx] = k;
         }
         worklist_push(huge ? 1u : 0u, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
 }
 
 struct SecondPassArgs {
-    double* sin_out;
+    double* sin_out;   // either may be null (single-output launches); the stash is in sin_out if present, else cos_out
     double* cos_out;
     long long* k_out;
     uint32_t n;
@@ -234,8 +237,8 @@ __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t
     uint64_t sb, cb;
     int64_t k;
     fabe13_sincos_one<CORE>(xb, table, &sb, &cb, &k);
-    a.sin_out[idx] = __longlong_as_double((long long)sb);
-    a.cos_out[idx] = __longlong_as_double((long long)cb);
+    if (a.sin_out) a.sin_out[idx] = __longlong_as_double((long long)sb);
+    if (a.cos_out) a.cos_out[idx] = __longlong_as_double((long long)cb);
     if (a.k_out) a.k_out[idx] = k;
 }
 
@@ -275,19 +278,20 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
 
     const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x;
     const uint32_t stride = gridDim.x * kThreads;
+    const double* stash = a.sin_out ? a.sin_out : a.cos_out;
     for (uint32_t i = gtid; i < total; i += stride) {
         uint32_t seg = 0;  // largest seg with seg_start[seg] <= i
 #pragma unroll
         for (int step = kSegments / 2; step > 0; step >>= 1)
             if (seg_start[seg + step] <= i) seg += step;
         const uint32_t idx = a.wl.entries[(size_t)seg * a.wl.seg_cap + (i - seg_start[seg])];
-        const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[idx]);
+        const uint64_t xb = (uint64_t)__double_as_longlong(stash[idx]);
         // still a stashed argument?  (when the rescan below is active another thread may already have reduced it)
         if (is_stashed(xb)) reduce_stashed<CORE>(a, idx, xb, table);
     }
     if (overflowed) {
         for (uint32_t i = gtid; i < a.n; i += stride) {
-            const uint64_t xb = (uint64_t)__double_as_longlong(a.sin_out[i]);
+            const uint64_t xb = (uint64_t)__double_as_longlong(stash[i]);
             if (is_stashed(xb)) reduce_stashed<CORE>(a, i, xb, table);
         }
     }
@@ -304,8 +308,8 @@ __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* i
         uint64_t sb, cb;
         int64_t k;
         fabe13_sincos_one<CORE>(xb, table, &sb, &cb, &k);
-        sin_out[i] = __longlong_as_double((long long)sb);
-        cos_out[i] = __longlong_as_double((long long)cb);
+        if (sin_out) sin_out[i] = __longlong_as_double((long long)sb);
+        if (cos_out) cos_out[i] = __longlong_as_double((long long)cb);
         if (k_out) k_out[i] = k;
     }
 }
@@ -337,23 +341,31 @@ __global__ void __launch_bounds__(kThreads) fill_loguniform_kernel(double* out, 
     }
 }
 
-template <int CORE, int VEC, bool WITH_K>
+template <int CORE, int VEC, bool WITH_K, int OUT>
 cudaError_t launch_stream_unroll(const StreamArgs& a, int unroll, int grid, cudaStream_t stream) {
-    switch (unroll) {
-        case 2: sincos_stream_kernel<CORE, VEC, 2, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
-        case 4: sincos_stream_kernel<CORE, VEC, 4, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
-        default: sincos_stream_kernel<CORE, VEC, 1, WITH_K><<<grid, kThreads, 0, stream>>>(a); break;
-    }
+    if (unroll == 2)
+        sincos_stream_kernel<CORE, VEC, 2, WITH_K, OUT><<<grid, kThreads, 0, stream>>>(a);
+    else
+        sincos_stream_kernel<CORE, VEC, 1, WITH_K, OUT><<<grid, kThreads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int CORE, bool WITH_K>
+template <int CORE, bool WITH_K, int OUT>
 cudaError_t launch_stream_vec(const StreamArgs& a, int vec, int unroll, int grid, cudaStream_t stream) {
     switch (vec) {
-        case 4: return launch_stream_unroll<CORE, 4, WITH_K>(a, unroll, grid, stream);
-        case 2: return launch_stream_unroll<CORE, 2, WITH_K>(a, unroll, grid, stream);
-        default: return launch_stream_unroll<CORE, 1, WITH_K>(a, unroll, grid, stream);
+        case 4: return launch_stream_unroll<CORE, 4, WITH_K, OUT>(a, unroll, grid, stream);
+        case 2: return launch_stream_unroll<CORE, 2, WITH_K, OUT>(a, unroll, grid, stream);
+        default: return launch_stream_unroll<CORE, 1, WITH_K, OUT>(a, unroll, grid, stream);
     }
+}
+
+template <int CORE>
+cudaError_t launch_stream(const StreamArgs& a, int vec, int unroll, int grid, cudaStream_t stream) {
+    if (a.sin_out && a.cos_out)
+        return a.k_out ? launch_stream_vec<CORE, true, OUT_BOTH>(a, vec, unroll, grid, stream)
+                       : launch_stream_vec<CORE, false, OUT_BOTH>(a, vec, unroll, grid, stream);
+    if (a.sin_out) return launch_stream_vec<CORE, false, OUT_SIN>(a, vec, unroll, grid, stream);
+    return launch_stream_vec<CORE, false, OUT_COS>(a, vec, unroll, grid, stream);
 }
 
 uint32_t segment_capacity(size_t n, const LaunchTuning& t) {
@@ -375,7 +387,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     }
 
     // widest vector all arrays can share: they must be congruent modulo the vector size
-    const uintptr_t pi = (uintptr_t)d_in, ps = (uintptr_t)d_sin, pc = (uintptr_t)d_cos;
+    const uintptr_t pi = (uintptr_t)d_in, ps = (uintptr_t)(d_sin ? d_sin : d_cos), pc = (uintptr_t)(d_cos ? d_cos : d_sin);
     int vec = 1;
     for (int v = 4; v > 1; v >>= 1) {
         const uintptr_t mask = (uintptr_t)v * 8 - 1;
@@ -387,7 +399,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     const uintptr_t vbytes = (uintptr_t)vec * 8;
     uint32_t head = (uint32_t)(((vbytes - (pi & (vbytes - 1))) & (vbytes - 1)) / 8);
     if (head > n) head = (uint32_t)n;
-    const int unroll = (t.unroll == 2 || t.unroll == 4) ? t.unroll : 1;
+    const int unroll = t.unroll == 2 ? 2 : 1;
 
     StreamArgs a;
     a.in = d_in;
@@ -411,8 +423,8 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     long long grid = ((long long)a.ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
     if (t.blocks_per_sm > 0 && grid > (long long)dev.sm_count * t.blocks_per_sm) grid = (long long)dev.sm_count * t.blocks_per_sm;
     if (grid < 1) grid = 1;
-    err = d_k ? launch_stream_vec<CORE, true>(a, vec, unroll, (int)grid, stream)
-              : launch_stream_vec<CORE, false>(a, vec, unroll, (int)grid, stream);
+    if (d_k && !(d_sin && d_cos)) return cudaErrorInvalidValue;  // the k hook exists for the sincos entry only
+    err = launch_stream<CORE>(a, vec, unroll, (int)grid, stream);
     if (err != cudaSuccess) return err;
 
     SecondPassArgs b;
@@ -450,7 +462,7 @@ cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long
                           const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                           int* launches) {
     if (n == 0) return cudaSuccess;
-    if (n > ((size_t)1 << 31)) return cudaErrorInvalidValue;
+    if (n > ((size_t)1 << 31) || (!d_sin && !d_cos)) return cudaErrorInvalidValue;
     if (core == FABE13_CORE_PSI)
         return launch_core<FABE13_CORE_PSI>(d_in, d_sin, d_cos, d_k, n, tuning, dev, workspace, stream, launches);
     return launch_core<FABE13_CORE_POLY>(d_in, d_sin, d_cos, d_k, n, tuning, dev, workspace, stream, launches);

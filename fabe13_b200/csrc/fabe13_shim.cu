@@ -68,7 +68,7 @@ const OptionDesc kOptions[] = {
     {"blocks_per_sm", "FABE13_CUDA_BLOCKS_PER_SM", &Config::blocks_per_sm, 0, 64},
     {"tiles_per_block", "FABE13_CUDA_TILES_PER_BLOCK", &Config::tiles_per_block, 1, 1024},
     {"second_pass_blocks_per_sm", "FABE13_CUDA_SECOND_PASS_BLOCKS_PER_SM", &Config::second_pass_blocks_per_sm, 1, 32},
-    {"unroll", "FABE13_CUDA_UNROLL", &Config::unroll, 1, 4},
+    {"unroll", "FABE13_CUDA_UNROLL", &Config::unroll, 1, 2},
     {"small_n", "FABE13_CUDA_SMALL_N", &Config::small_n, 0, (long long)1 << 30},
     {"worklist_shift", "FABE13_CUDA_WORKLIST_SHIFT", &Config::worklist_shift, 0, 20},
     {"chunk_elems", "FABE13_CUDA_CHUNK_ELEMS", &Config::chunk_elems, 1024, (long long)1 << 28},
@@ -212,8 +212,8 @@ int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k,
             }
         }
         int launches = 0;
-        cudaError_t e = fabe13::launch_sincos(d_in + off, d_sin + off, d_cos + off, d_k ? d_k + off : nullptr, m, core,
-                                              t, ds->info, ws, stream, &launches);
+        cudaError_t e = fabe13::launch_sincos(d_in + off, d_sin ? d_sin + off : nullptr, d_cos ? d_cos + off : nullptr,
+                                              d_k ? d_k + off : nullptr, m, core, t, ds->info, ws, stream, &launches);
         g_launches.fetch_add((unsigned long long)launches);
         if (pooled) {
             cudaError_t e2 = cudaFreeAsync(ws, stream);
@@ -304,12 +304,12 @@ int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, 
                   const LaunchTuning& t, int core) {
     FABE13_TRY(cudaMemcpyAsync(sl.d_in, src, m * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
     int launches = 0;
-    cudaError_t e = fabe13::launch_sincos(sl.d_in, sl.d_sin, sl.d_cos, nullptr, m, core, t, s.info,
-                                          m >= (size_t)t.small_n ? sl.d_ws : nullptr, sl.stream, &launches);
+    cudaError_t e = fabe13::launch_sincos(sl.d_in, dst_sin ? sl.d_sin : nullptr, dst_cos ? sl.d_cos : nullptr, nullptr, m, core,
+                                          t, s.info, m >= (size_t)t.small_n ? sl.d_ws : nullptr, sl.stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
     if (e != cudaSuccess) return record(e, "launch_sincos(host path)");
-    FABE13_TRY(cudaMemcpyAsync(dst_sin, sl.d_sin, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
-    FABE13_TRY(cudaMemcpyAsync(dst_cos, sl.d_cos, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    if (dst_sin) FABE13_TRY(cudaMemcpyAsync(dst_sin, sl.d_sin, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    if (dst_cos) FABE13_TRY(cudaMemcpyAsync(dst_cos, sl.d_cos, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
     return 0;
 }
 
@@ -321,7 +321,7 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
                const LaunchTuning& t, int core) {
     if (!s.small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&s.small_stream, cudaStreamNonBlocking));
     const double* src = in;
-    double *dst_s = sin_out, *dst_c = cos_out;
+    double *dst_s = sin_out, *dst_c = cos_out;  // either may be null (single-output calls)
     if (!pinned) {
         if (s.small_cap < n) {
             if (s.small_stage) cudaFreeHost(s.small_stage);
@@ -333,12 +333,13 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
         }
         memcpy(s.small_stage, in, n * sizeof(double));
         src = s.small_stage;
-        dst_s = s.small_stage + s.small_cap;
-        dst_c = s.small_stage + 2 * s.small_cap;
+        if (sin_out) dst_s = s.small_stage + s.small_cap;
+        if (cos_out) dst_c = s.small_stage + 2 * s.small_cap;
     }
-    void *d_in, *d_s, *d_c;
-    if (cudaHostGetDevicePointer(&d_in, (void*)src, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_s, dst_s, 0) != cudaSuccess ||
-        cudaHostGetDevicePointer(&d_c, dst_c, 0) != cudaSuccess) {
+    void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
+    if (cudaHostGetDevicePointer(&d_in, (void*)src, 0) != cudaSuccess ||
+        (dst_s && cudaHostGetDevicePointer(&d_s, dst_s, 0) != cudaSuccess) ||
+        (dst_c && cudaHostGetDevicePointer(&d_c, dst_c, 0) != cudaSuccess)) {
         (void)cudaGetLastError();
         return -1;
     }
@@ -351,8 +352,8 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
     if (e != cudaSuccess) return record(e, "launch_sincos(zero-copy)");
     FABE13_TRY(cudaStreamSynchronize(s.small_stream));
     if (!pinned) {
-        memcpy(sin_out, dst_s, n * sizeof(double));
-        memcpy(cos_out, dst_c, n * sizeof(double));
+        if (sin_out) memcpy(sin_out, dst_s, n * sizeof(double));
+        if (cos_out) memcpy(cos_out, dst_c, n * sizeof(double));
     }
     return 0;
 }
@@ -378,7 +379,8 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
         for (size_t i = 0; i < nchunks; ++i) {
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
-            if (int rc = enqueue_chunk(*ds, ds->slots[i % kSlots], in + off, sin_out + off, cos_out + off, m, t, core))
+            if (int rc = enqueue_chunk(*ds, ds->slots[i % kSlots], in + off, sin_out ? sin_out + off : nullptr,
+                                       cos_out ? cos_out + off : nullptr, m, t, core))
                 return rc;
         }
         if (n >= ((size_t)1 << 22)) {
@@ -410,7 +412,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
             memcpy(sl.h_in, in + off, m * sizeof(double));
-            int rc = enqueue_chunk(*ds, sl, sl.h_in, sl.h_sin, sl.h_cos, m, t, core);
+            int rc = enqueue_chunk(*ds, sl, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core);
             if (rc == 0) {
                 cudaError_t e = cudaEventRecord(sl.done, sl.stream);
                 if (e == cudaSuccess) e = cudaEventSynchronize(sl.done);  // blocking event: the worker sleeps
@@ -420,8 +422,8 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
                 rc_all.store(rc);
                 return;
             }
-            memcpy(sin_out + off, sl.h_sin, m * sizeof(double));
-            memcpy(cos_out + off, sl.h_cos, m * sizeof(double));
+            if (sin_out) memcpy(sin_out + off, sl.h_sin, m * sizeof(double));
+            if (cos_out) memcpy(cos_out + off, sl.h_cos, m * sizeof(double));
         }
     };
     if (workers <= 1) {
@@ -438,7 +440,10 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
 int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
     if (n == 0) return 0;
     load_env();
-    const PtrKind ki = classify(in), ks = classify(sin_out), kc = classify(cos_out);
+    if (!sin_out && !cos_out) return record(cudaErrorInvalidValue, "no output array");
+    const PtrKind ki = classify(in);
+    const PtrKind ks = sin_out ? classify(sin_out) : classify(cos_out);
+    const PtrKind kc = cos_out ? classify(cos_out) : ks;
     if (ki == PTR_DEVICE || ks == PTR_DEVICE || kc == PTR_DEVICE) {
         if (!(ki == PTR_DEVICE && ks == PTR_DEVICE && kc == PTR_DEVICE))
             return record(cudaErrorInvalidValue, "fabe13_sincos: mixed host and device pointers");
@@ -467,7 +472,8 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
                 rcs[(size_t)g] = record(cudaErrorInvalidDevice, "cudaSetDevice(slice)");
                 return;
             }
-            if (e > b) rcs[(size_t)g] = host_slice(dev, in + b, sin_out + b, cos_out + b, e - b, pinned);
+            if (e > b)
+                rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned);
         });
     }
     for (std::thread& x : th) x.join();
@@ -557,6 +563,26 @@ double fabe13_acos(double x) { return acos(x); }
 
 int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream) {
     return run_device(d_in, d_sin, d_cos, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+}
+
+// single-output array variants (the array forms of fabe13_sin / fabe13_cos): 16 B/element instead of 24
+int fabe13_sin_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
+    if (!d_out && n) return record(cudaErrorInvalidValue, "fabe13_sin_device: null output");
+    return run_device(d_in, d_out, nullptr, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+}
+int fabe13_cos_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
+    if (!d_out && n) return record(cudaErrorInvalidValue, "fabe13_cos_device: null output");
+    return run_device(d_in, nullptr, d_out, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+}
+int fabe13_sin_host(const double* in, double* out, size_t n) {
+    if (n == 0) return 0;
+    if (!out) return record(cudaErrorInvalidValue, "fabe13_sin_host: null output");
+    return run_host(in, out, nullptr, n);
+}
+int fabe13_cos_host(const double* in, double* out, size_t n) {
+    if (n == 0) return 0;
+    if (!out) return record(cudaErrorInvalidValue, "fabe13_cos_host: null output");
+    return run_host(in, nullptr, out, n);
 }
 
 int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,

@@ -31,6 +31,14 @@ int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_
 int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
                            void* cuda_stream);
 
+/* Array forms of fabe13_sin / fabe13_cos (reference scalar API fabe13/fabe13.h:71-72): one output array, 16 bytes of
+ * traffic per element instead of 24.  Same numerics as fabe13_sincos (bit-identical values).  Device pointers on a
+ * stream, or host pointers (synchronous), exactly as the sincos entries. */
+int fabe13_sin_device(const double* d_in, double* d_out, size_t n, void* cuda_stream);
+int fabe13_cos_device(const double* d_in, double* d_out, size_t n, void* cuda_stream);
+int fabe13_sin_host(const double* in, double* out, size_t n);
+int fabe13_cos_host(const double* in, double* out, size_t n);
+
 /* Same as fabe13_sincos_device with caller-provided scratch of at least fabe13_sincos_workspace_bytes(n) bytes
  * (no allocation on the call path; usable inside CUDA graph capture on any toolkit). */
 size_t fabe13_sincos_workspace_bytes(size_t n);
@@ -58,7 +66,7 @@ void fabe13_cuda_host_free(void* p);
  * multiples of 4 elements so every slice keeps 32-byte alignment.  The remainder goes to the last rank. */
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
 
-/* Options: "core" (0/1), "unroll" (1/2/4), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
+/* Options: "core" (0/1), "unroll" (1/2), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
  * per SM), "second_pass_blocks_per_sm", "small_n", "worklist_shift", "chunk_elems", "host_devices", "stage_threads", "zero_copy_max", "tiles_per_block".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);

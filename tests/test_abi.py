@@ -85,8 +85,8 @@ def test_shard_bounds_cover_and_align(fabe13):
 
 def test_options_roundtrip_and_validation(fabe13):
     old = fabe13.get_option("unroll")
-    fabe13.set_option("unroll", 4)
-    assert fabe13.get_option("unroll") == 4
+    fabe13.set_option("unroll", 2)
+    assert fabe13.get_option("unroll") == 2
     fabe13.set_option("unroll", old)
     with pytest.raises(ValueError):
         fabe13.set_option("unroll", 99)
