@@ -279,20 +279,36 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
     const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x;
     const uint32_t stride = gridDim.x * kThreads;
     const double* stash = a.sin_out ? a.sin_out : a.cos_out;
-    for (uint32_t i = gtid; i < total; i += stride) {
+    // Both loops are software-pipelined: the loads of the next iteration (index two steps ahead, argument one step
+    // ahead) are in flight while the ~250-instruction reduction of the current element runs.
+    auto entry = [&](uint32_t i) -> uint32_t {
+        if (i >= total) return 0;
         uint32_t seg = 0;  // largest seg with seg_start[seg] <= i
 #pragma unroll
         for (int step = kSegments / 2; step > 0; step >>= 1)
             if (seg_start[seg + step] <= i) seg += step;
-        const uint32_t idx = a.wl.entries[(size_t)seg * a.wl.seg_cap + (i - seg_start[seg])];
-        const uint64_t xb = (uint64_t)__double_as_longlong(stash[idx]);
-        // still a stashed argument?  (when the rescan below is active another thread may already have reduced it)
-        if (is_stashed(xb)) reduce_stashed<CORE>(a, idx, xb, table);
+        return a.wl.entries[(size_t)seg * a.wl.seg_cap + (i - seg_start[seg])];
+    };
+    auto load_bits = [&](uint32_t idx) -> uint64_t { return (uint64_t)__double_as_longlong(stash[idx]); };
+    if (gtid < total) {
+        uint32_t idx0 = entry(gtid), idx1 = entry(gtid + stride);
+        uint64_t x0 = load_bits(idx0);
+        for (uint32_t i = gtid; i < total; i += stride) {
+            const uint32_t idx2 = entry(i + 2 * stride);
+            const uint64_t x1 = (i + stride < total) ? load_bits(idx1) : 0;
+            // still a stashed argument?  (when the rescan below is active another thread may already have reduced it)
+            if (is_stashed(x0)) reduce_stashed<CORE>(a, idx0, x0, table);
+            idx0 = idx1;
+            idx1 = idx2;
+            x0 = x1;
+        }
     }
-    if (overflowed) {
+    if (overflowed && gtid < a.n) {
+        uint64_t x0 = load_bits(gtid);
         for (uint32_t i = gtid; i < a.n; i += stride) {
-            const uint64_t xb = (uint64_t)__double_as_longlong(stash[i]);
-            if (is_stashed(xb)) reduce_stashed<CORE>(a, i, xb, table);
+            const uint64_t x1 = (i + stride < a.n) ? load_bits(i + stride) : 0;
+            if (is_stashed(x0)) reduce_stashed<CORE>(a, i, x0, table);
+            x0 = x1;
         }
     }
 }
