@@ -46,6 +46,7 @@ def build_library(force=False, verbose=False):
         # host side: keep * and + as separate roundings (the host scalar API must match the device bit for bit)
         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-mfma,-fvisibility=hidden",
         "-Xptxas", "-v" if verbose else "-O3",
+    ] + [f"-D{d}" for d in os.environ.get("FABE13_BUILD_DEFINES", "").split() if d] + [
         "-o", LIBPATH,
     ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
