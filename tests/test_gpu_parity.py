@@ -517,3 +517,47 @@ def test_sin_only_cos_only_host(fabe13, cuda, oracle, n):
     assert np.array_equal(bits(po.array), bits(s))
     px.free()
     po.free()
+
+
+def test_entry_points_are_thread_safe(fabe13, cuda, oracle):
+    """Reference contract: every entry point is re-entrant.  Four host threads hammer the device entry
+    (own streams), the pinned and pageable host entries and the scalar API at the same time."""
+    import threading
+
+    import torch
+
+    errors = []
+    xs = [oracle.fill_uniform(1_500_000 + 1000 * t, 400 + t, -1e5, 1e5) for t in range(4)]
+    for x in xs:
+        x[::1001] = 1e300
+    want = [fabe13.host_core(x, 0) for x in xs]
+
+    def worker(t):
+        try:
+            x = xs[t]
+            hs, hc, _ = want[t]
+            with torch.cuda.stream(torch.cuda.Stream()):
+                xt = torch.from_numpy(x).to(cuda)
+                for it in range(6):
+                    if (t + it) % 3 == 0:
+                        s, c = fabe13.sincos(x)  # pageable host path (staging threads inside)
+                        ok = np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
+                    elif (t + it) % 3 == 1:
+                        s, c = fabe13.sincos(xt)
+                        torch.cuda.current_stream().synchronize()
+                        ok = np.array_equal(bits(s.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
+                    else:
+                        s, c = fabe13.sincos(x[:5000])  # small host call: zero-copy kernel
+                        ok = np.array_equal(bits(s), bits(hs[:5000])) and np.array_equal(bits(c), bits(hc[:5000]))
+                    ok = ok and fabe13.sin(float(x[it])) == hs[it]
+                    if not ok:
+                        errors.append((t, it))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
