@@ -561,3 +561,21 @@ def test_entry_points_are_thread_safe(fabe13, cuda, oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_torch_ops_registration(fabe13, cuda, oracle):
+    """torch.ops.fabe13.sincos / sin / cos on CUDA and CPU tensors, incl. a non-contiguous view."""
+    import torch
+
+    import fabe13_b200.torch_ops  # noqa: F401  (registers the operators)
+
+    x = oracle.fill_uniform(300_000, 501, -1e5, 1e5).reshape(300, 1000)
+    hs, hc, _ = fabe13.host_core(x.ravel(), 0)
+    for dev in (cuda, torch.device("cpu")):
+        xt = torch.from_numpy(x).to(dev)
+        s, c = torch.ops.fabe13.sincos(xt)
+        assert s.shape == xt.shape
+        assert np.array_equal(bits(s.cpu().numpy().ravel()), bits(hs)) and np.array_equal(bits(c.cpu().numpy().ravel()), bits(hc))
+        assert torch.equal(torch.ops.fabe13.sin(xt), s) and torch.equal(torch.ops.fabe13.cos(xt), c)
+        st, _ = torch.ops.fabe13.sincos(xt.t())  # non-contiguous input
+        assert torch.equal(st, s.t())
