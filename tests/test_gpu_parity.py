@@ -579,3 +579,27 @@ def test_torch_ops_registration(fabe13, cuda, oracle):
         assert torch.equal(torch.ops.fabe13.sin(xt), s) and torch.equal(torch.ops.fabe13.cos(xt), c)
         st, _ = torch.ops.fabe13.sincos(xt.t())  # non-contiguous input
         assert torch.equal(st, s.t())
+
+
+def test_host_array_split_over_all_gpus(fabe13, cuda, oracle):
+    """option host_devices: one contiguous slice of a HOST array per GPU, one pipeline each (host-resident)."""
+    import torch
+
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("single-GPU box")
+    old = fabe13.get_option("host_devices")
+    fabe13.set_option("host_devices", ndev)
+    try:
+        n = 9_000_001
+        x = oracle.fill_uniform(n, 601, -1e5, 1e5)
+        x[::5003] = 1e200
+        s, c = fabe13.sincos(x)
+        px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
+        px.array[:] = x
+        fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)
+        hs, hc, _ = fabe13.host_core(x, 0)
+        assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
+        assert np.array_equal(bits(ps.array), bits(hs)) and np.array_equal(bits(pc.array), bits(hc))
+    finally:
+        fabe13.set_option("host_devices", old)
