@@ -255,22 +255,32 @@ void free_slots(DeviceState& s) {
     }
     s.chunk_cap = 0;
     s.stage_cap = 0;
+    s.ws_bytes = 0;
 }
 
 // (re)size the slots of the current device for `chunk` elements; pinned staging only if asked for
 int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning& t) {
     if (s.chunk_cap < chunk) {
         free_slots(s);
-        s.ws_bytes = fabe13::workspace_bytes(chunk, t);
         for (Slot& sl : s.slots) {
             if (!sl.stream) FABE13_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
             if (!sl.done) FABE13_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventBlockingSync | cudaEventDisableTiming));
             FABE13_TRY(cudaMalloc(&sl.d_in, chunk * sizeof(double)));
             FABE13_TRY(cudaMalloc(&sl.d_sin, chunk * sizeof(double)));
             FABE13_TRY(cudaMalloc(&sl.d_cos, chunk * sizeof(double)));
-            FABE13_TRY(cudaMalloc(&sl.d_ws, s.ws_bytes));
         }
         s.chunk_cap = chunk;
+    }
+    // the worklist scratch depends on the tuning in force (option worklist_shift may change between calls)
+    const size_t need_ws = fabe13::workspace_bytes(s.chunk_cap, t);
+    if (s.ws_bytes < need_ws) {
+        for (Slot& sl : s.slots) {
+            if (sl.d_ws) FABE13_TRY(cudaFree(sl.d_ws));
+            sl.d_ws = nullptr;
+        }
+        s.ws_bytes = 0;
+        for (Slot& sl : s.slots) FABE13_TRY(cudaMalloc(&sl.d_ws, need_ws));
+        s.ws_bytes = need_ws;
     }
     if (staging && s.stage_cap < chunk) {
         for (Slot& sl : s.slots) {

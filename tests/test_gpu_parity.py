@@ -603,3 +603,25 @@ def test_host_array_split_over_all_gpus(fabe13, cuda, oracle):
         assert np.array_equal(bits(ps.array), bits(hs)) and np.array_equal(bits(pc.array), bits(hc))
     finally:
         fabe13.set_option("host_devices", old)
+
+
+def test_host_path_survives_tuning_changes_between_calls(fabe13, cuda, oracle):
+    """The host pipeline caches device scratch; changing worklist_shift / chunk size between calls must resize it."""
+    n = 6_000_000
+    x = oracle.fill_uniform(n, 701, -1e4, 1e4)
+    x[::3] = oracle.fill_loguniform((n + 2) // 3, 702)
+    hs, hc, _ = fabe13.host_core(x, 0)
+    old_chunk = fabe13.get_option("chunk_elems")
+    try:
+        for shift, chunk in ((3, 1 << 22), (0, 1 << 22), (20, 1 << 23), (0, 1 << 23)):
+            fabe13.set_option("worklist_shift", shift)
+            fabe13.set_option("chunk_elems", chunk)
+            fabe13.set_option("small_n", 0)
+            px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
+            px.array[:] = x
+            fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)
+            assert np.array_equal(bits(ps.array), bits(hs)) and np.array_equal(bits(pc.array), bits(hc)), (shift, chunk)
+            for p in (px, ps, pc):
+                p.free()
+    finally:
+        fabe13.set_option("chunk_elems", old_chunk)
