@@ -60,14 +60,29 @@ struct Fabe13Coef {
             -FABE13_PIO2_2, -FABE13_PIO2_3, FABE13_S1, FABE13_S2, FABE13_S3, FABE13_S4, FABE13_S5, FABE13_S6, FABE13_C1, \
             FABE13_C2, FABE13_C3, FABE13_C4, FABE13_C5, FABE13_C6, -0.5, 1.0                                           \
     }
+// the Psi-Hyperbasis core's constants (reference cubics with their signs folded in, fitted correction polynomials)
+struct Fabe13PsiCoef {
+    double three_eighths, one;
+    double a2, neg_a3, neg_a1, b2, neg_b3, neg_b1;
+    double ds[FABE13_PSI_CORR_TERMS], dc[FABE13_PSI_CORR_TERMS];
+};
+#define FABE13_PSI_COEF_INIT                                                                                     \
+    {                                                                                                            \
+        0.375, 1.0, FABE13_HX_A2, -FABE13_HX_A3, -FABE13_HX_A1, FABE13_HX_B2, -FABE13_HX_B3, -FABE13_HX_B1, FABE13_PSI_DS, \
+            FABE13_PSI_DC                                                                                        \
+    }
 #if defined(__CUDACC__)
 static __constant__ Fabe13Coef fabe13_coef_device = FABE13_COEF_INIT;
+static __constant__ Fabe13PsiCoef fabe13_psi_coef_device = FABE13_PSI_COEF_INIT;
 #endif
 static const Fabe13Coef fabe13_coef_host = FABE13_COEF_INIT;
+static const Fabe13PsiCoef fabe13_psi_coef_host = FABE13_PSI_COEF_INIT;
 #if defined(__CUDA_ARCH__)
 #define FABE13_CF(field) (fabe13_coef_device.field)
+#define FABE13_PCF(field) (fabe13_psi_coef_device.field)
 #else
 #define FABE13_CF(field) (fabe13_coef_host.field)
+#define FABE13_PCF(field) (fabe13_psi_coef_host.field)
 #endif
 
 #define FABE13_QNAN_BITS 0x7FF8000000000000ull
@@ -256,27 +271,25 @@ FABE13_HD void fabe13_core_poly(double r, double* s, double* c) {
 //     Pa/Pb are the reference's Taylor-matched cubics; Ds/Dc are fitted in tools/gen_constants.py.
 // ---------------------------------------------------------------------------------------------------------------
 FABE13_HD void fabe13_core_psi(double r, double* s, double* c) {
-    const double ds[FABE13_PSI_CORR_TERMS] = FABE13_PSI_DS;
-    const double dc[FABE13_PSI_CORR_TERMS] = FABE13_PSI_DC;
     const double z = FABE13_MUL(r, r);
-    const double den = FABE13_FMA(0.375, z, 1.0);
+    const double den = FABE13_FMA(FABE13_PCF(three_eighths), z, FABE13_PCF(one));
     const double psi = r / den;  // IEEE-754 correctly rounded on both sides
     const double p = FABE13_MUL(psi, psi);
-    double pa = FABE13_FMA(-FABE13_HX_A3, p, FABE13_HX_A2);
-    double pb = FABE13_FMA(-FABE13_HX_B3, p, FABE13_HX_B2);
-    pa = FABE13_FMA(pa, p, -FABE13_HX_A1);
-    pb = FABE13_FMA(pb, p, -FABE13_HX_B1);
-    pa = FABE13_FMA(pa, p, 1.0);
-    const double cos_psi = FABE13_FMA(pb, p, 1.0);
+    double pa = FABE13_FMA(FABE13_PCF(neg_a3), p, FABE13_PCF(a2));
+    double pb = FABE13_FMA(FABE13_PCF(neg_b3), p, FABE13_PCF(b2));
+    pa = FABE13_FMA(pa, p, FABE13_PCF(neg_a1));
+    pb = FABE13_FMA(pb, p, FABE13_PCF(neg_b1));
+    pa = FABE13_FMA(pa, p, FABE13_PCF(one));
+    const double cos_psi = FABE13_FMA(pb, p, FABE13_PCF(one));
     const double sin_psi = FABE13_MUL(psi, pa);
-    double qs = ds[FABE13_PSI_CORR_TERMS - 1];
-    double qc = dc[FABE13_PSI_CORR_TERMS - 1];
+    double qs = FABE13_PCF(ds)[FABE13_PSI_CORR_TERMS - 1];
+    double qc = FABE13_PCF(dc)[FABE13_PSI_CORR_TERMS - 1];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = FABE13_PSI_CORR_TERMS - 2; i >= 0; --i) {
-        qs = FABE13_FMA(z, qs, ds[i]);
-        qc = FABE13_FMA(z, qc, dc[i]);
+        qs = FABE13_FMA(z, qs, FABE13_PCF(ds)[i]);
+        qc = FABE13_FMA(z, qc, FABE13_PCF(dc)[i]);
     }
     const double rz = FABE13_MUL(r, z);
     const double zz = FABE13_MUL(z, z);

@@ -625,3 +625,24 @@ def test_host_path_survives_tuning_changes_between_calls(fabe13, cuda, oracle):
                 p.free()
     finally:
         fabe13.set_option("chunk_elems", old_chunk)
+
+
+def test_c5_edge_sweep_full_size_cyclic(fabe13, cuda, oracle, golden):
+    """C5 at N ~ 1e9: the edge pool (specials, RN(m*pi/2) +- 2 ulp, odd multiples of pi/4, subnormal ramp, a few
+    Payne-Hanek arguments) repeated cyclically.  One period is checked against the oracle; every other period must
+    reproduce it bit for bit (position independence at full size, with ~0.1% of the lanes going through the
+    ballot / worklist / second pass)."""
+    import torch
+
+    pool = np.concatenate([edge_pattern(golden, 6173), np.array([1e22, -1e300, 2.0 ** 45, 1.7976931348623157e308, -2.0 ** 1023])])
+    period = pool.size
+    rows = 1_000_000_000 // period
+    x = torch.from_numpy(pool).to(cuda).repeat(rows)
+    s, c = fabe13.sincos(x)
+    torch.cuda.synchronize()
+    s0 = s[:period].cpu().numpy()
+    c0 = c[:period].cpu().numpy()
+    check_against_oracle(pool, s0, c0, None, oracle, label="C5 full size, first period")
+    sv = s.view(rows, period).view(torch.int64)
+    cv = c.view(rows, period).view(torch.int64)
+    assert bool((sv == sv[0]).all()) and bool((cv == cv[0]).all())
