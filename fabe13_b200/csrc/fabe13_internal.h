@@ -12,6 +12,7 @@ struct LaunchTuning {
     int threads;        // threads per block of the streaming kernel (multiple of 32)
     int blocks_per_sm;  // 0 = one tile per block (default); k > 0 = persistent grid of SMs * k blocks
     int tiles_per_block;  // consecutive tiles per block per grid-stride step
+    int pdl;              // 1 = queue the launches of one call with programmatic dependent launch
     int second_pass_blocks_per_sm;  // grid of the Payne-Hanek second pass
     int unroll;         // 256-bit vectors in flight per thread: 1 or 2
     int small_n;        // n below this runs the single inline kernel (no worklist, one launch)

@@ -19,6 +19,7 @@
 // workspace = { kSegments counters, 128 B apart } { kSegments x seg_cap u32 element indices }.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "fabe13_core.h"
 #include "fabe13_internal.h"
@@ -34,6 +35,17 @@ constexpr int kCounterStrideWords = 32;
 constexpr int kWorklistHeaderBytes = kSegments * kCounterStrideWords * 4;
 
 __constant__ uint64_t c_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
+
+// Programmatic dependent launch: the three launches of one call (zero the counters, stream, second pass) are queued
+// with the programmatic-serialisation attribute, so each one is staged while its predecessor still runs and the
+// 2-4 us launch gaps between dependent kernels disappear.  A kernel launched that way must not touch what its
+// predecessor produces before this wait (all prerequisite grids complete, their writes visible).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__global__ void __launch_bounds__(1024) zero_counters_kernel(unsigned int* counters) {
+    counters[threadIdx.x] = 0;  // kSegments * kCounterStrideWords == 1024 words
+}
+static_assert(kSegments * kCounterStrideWords == 1024, "zero_counters_kernel clears exactly one 1024-word header");
 
 struct Worklist {
     unsigned int* counters;  // kSegments counters, kCounterStrideWords apart; may exceed seg_cap (= overflow)
@@ -54,6 +66,7 @@ struct StreamArgs {
     uint32_t nvec;     // vectors in the body
     uint32_t ntiles;   // tiles of kThreads*UNROLL vectors
     uint32_t tiles_per_block;  // consecutive tiles one block takes per grid-stride step
+    bool pdl;                  // launched with programmatic stream serialisation
     Worklist wl;
 };
 
@@ -124,6 +137,7 @@ __device__ __forceinline__ void worklist_push(uint32_t mine, const Worklist& wl,
     }
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     if (total == 0) return;
+    grid_dependency_wait();  // the counters must have been zeroed (the stream kernel may have been launched early)
     const uint32_t seg = blockIdx.x % kSegments;
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(wl.counters + seg * kCounterStrideWords, total);
@@ -257,6 +271,7 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
     __shared__ uint64_t table[FABE13_PH_WORDS];
     __shared__ uint32_t seg_start[kSegments + 1];
     __shared__ int overflowed;
+    grid_dependency_wait();  // everything below reads what the stream kernel wrote
     if (threadIdx.x < 32) {
         const uint32_t lane = threadIdx.x;
         const uint32_t raw = a.wl.counters[lane * kCounterStrideWords];
@@ -357,13 +372,26 @@ __global__ void __launch_bounds__(kThreads) fill_loguniform_kernel(double* out, 
     }
 }
 
+// Launch `kernel(arg)`; with `dependent` the launch carries the programmatic-stream-serialisation attribute.
+template <typename Arg>
+cudaError_t launch_1arg(void (*kernel)(Arg), const Arg& arg, int grid, int block, cudaStream_t stream, bool dependent) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = dependent ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+
 template <int CORE, int VEC, bool WITH_K, int OUT>
 cudaError_t launch_stream_unroll(const StreamArgs& a, int unroll, int grid, cudaStream_t stream) {
-    if (unroll == 2)
-        sincos_stream_kernel<CORE, VEC, 2, WITH_K, OUT><<<grid, kThreads, 0, stream>>>(a);
-    else
-        sincos_stream_kernel<CORE, VEC, 1, WITH_K, OUT><<<grid, kThreads, 0, stream>>>(a);
-    return cudaGetLastError();
+    if (unroll == 2) return launch_1arg(sincos_stream_kernel<CORE, VEC, 2, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
+    return launch_1arg(sincos_stream_kernel<CORE, VEC, 1, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
 }
 
 template <int CORE, bool WITH_K, int OUT>
@@ -430,7 +458,14 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     a.wl.entries = (uint32_t*)((char*)workspace + kWorklistHeaderBytes);
     a.wl.seg_cap = segment_capacity(n, t);
 
-    cudaError_t err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
+    a.pdl = t.pdl != 0;
+    cudaError_t err;
+    if (a.pdl) {
+        zero_counters_kernel<<<1, 1024, 0, stream>>>(a.wl.counters);  // an ordinary launch: waits for all earlier work
+        err = cudaGetLastError();
+    } else {
+        err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
+    }
     if (err != cudaSuccess) return err;
 
     // blocks_per_sm == 0: one chunk of tiles_per_block tiles per block (the block scheduler walks the array in
@@ -449,9 +484,9 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     b.k_out = d_k;
     b.n = (uint32_t)n;
     b.wl = a.wl;
-    sincos_second_pass_kernel<CORE><<<dev.sm_count * t.second_pass_blocks_per_sm, kThreads, 0, stream>>>(b);
-    *launches += 2;
-    return cudaGetLastError();
+    err = launch_1arg(sincos_second_pass_kernel<CORE>, b, dev.sm_count * t.second_pass_blocks_per_sm, kThreads, stream, a.pdl);
+    *launches += a.pdl ? 3 : 2;
+    return err;
 }
 
 }  // namespace

@@ -41,6 +41,7 @@ struct Config {
     std::atomic<long long> core{FABE13_CORE_POLY};
     std::atomic<long long> blocks_per_sm{0};
     std::atomic<long long> tiles_per_block{1};
+    std::atomic<long long> pdl{1};
     std::atomic<long long> second_pass_blocks_per_sm{8};
     std::atomic<long long> unroll{1};
     std::atomic<long long> small_n{(long long)1 << 22};
@@ -67,6 +68,7 @@ const OptionDesc kOptions[] = {
     {"core", "FABE13_CUDA_CORE", &Config::core, 0, 1},
     {"blocks_per_sm", "FABE13_CUDA_BLOCKS_PER_SM", &Config::blocks_per_sm, 0, 64},
     {"tiles_per_block", "FABE13_CUDA_TILES_PER_BLOCK", &Config::tiles_per_block, 1, 1024},
+    {"pdl", "FABE13_CUDA_PDL", &Config::pdl, 0, 1},
     {"second_pass_blocks_per_sm", "FABE13_CUDA_SECOND_PASS_BLOCKS_PER_SM", &Config::second_pass_blocks_per_sm, 1, 32},
     {"unroll", "FABE13_CUDA_UNROLL", &Config::unroll, 1, 2},
     {"small_n", "FABE13_CUDA_SMALL_N", &Config::small_n, 0, (long long)1 << 30},
@@ -98,6 +100,7 @@ LaunchTuning current_tuning() {
     t.threads = 256;
     t.blocks_per_sm = (int)g_cfg.blocks_per_sm.load();
     t.tiles_per_block = (int)g_cfg.tiles_per_block.load();
+    t.pdl = (int)g_cfg.pdl.load();
     t.second_pass_blocks_per_sm = (int)g_cfg.second_pass_blocks_per_sm.load();
     t.unroll = (int)g_cfg.unroll.load();
     t.small_n = (int)g_cfg.small_n.load();

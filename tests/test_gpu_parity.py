@@ -40,7 +40,7 @@ def gpu_sincos(fabe13, cuda, x):
 
 @pytest.fixture(autouse=True)
 def _defaults(fabe13):
-    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift")}
+    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift", "pdl")}
     yield
     for k, v in saved.items():
         fabe13.set_option(k, v)
@@ -197,6 +197,29 @@ def test_c4_sparse_mix_uses_the_worklist(fabe13, cuda, oracle):
     big = np.abs(x) >= HUGE
     _, _, hk = fabe13.host_core(x[big & np.isfinite(x)], 0)
     assert np.array_equal(k[big & np.isfinite(x)], hk)
+
+
+@pytest.mark.parametrize("pdl", [0, 1])
+def test_programmatic_dependent_launch_on_and_off(fabe13, cuda, oracle, pdl):
+    """The three launches of a call are queued with programmatic stream serialisation (option pdl); results must not
+    depend on it, also when calls follow each other back to back on one stream with producers/consumers around."""
+    import torch
+
+    fabe13.set_option("pdl", pdl)
+    fabe13.set_option("small_n", 0)
+    n = 3_000_017
+    base = oracle.fill_uniform(n, 801, -1e5, 1e5)
+    base[::211] = oracle.fill_loguniform((n + 210) // 211, 802)
+    hs, hc, _ = fabe13.host_core(base, 0)
+    xt = torch.from_numpy(base).to(cuda)
+    for _ in range(5):
+        y = xt * 1.0                      # producer kernel on the same stream
+        s, c = fabe13.sincos(y)
+        acc = s + c                       # consumer kernel on the same stream
+        s2, c2 = fabe13.sincos(y)         # next call reuses pooled scratch immediately
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(s.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
+    assert np.array_equal(bits(s2.cpu().numpy()), bits(hs)) and np.array_equal(bits(acc.cpu().numpy()), bits(hs + hc))
 
 
 @pytest.mark.parametrize("shift", [0, 3, 20])
