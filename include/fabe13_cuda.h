@@ -67,7 +67,7 @@ void fabe13_cuda_host_free(void* p);
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
 
 /* Options: "core" (0/1), "unroll" (1/2), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
- * per SM), "second_pass_blocks_per_sm", "small_n", "worklist_shift", "chunk_elems", "host_devices", "stage_threads", "zero_copy_max", "tiles_per_block".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
+ * per SM), "second_pass_blocks_per_sm", "small_n", "worklist_shift", "chunk_elems", "host_devices", "stage_threads", "zero_copy_max", "tiles_per_block", "pdl" (programmatic dependent launch of the per-call kernels).  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);
 int fabe13_cuda_get_option(const char* key, long long* value);
