@@ -669,3 +669,30 @@ def test_c5_edge_sweep_full_size_cyclic(fabe13, cuda, oracle, golden):
     sv = s.view(rows, period).view(torch.int64)
     cv = c.view(rows, period).view(torch.int64)
     assert bool((sv == sv[0]).all()) and bool((cv == cv[0]).all())
+
+
+def test_more_than_one_launch_sequence(fabe13, cuda, oracle):
+    """n > 2^30 is split into several launch sequences (32-bit element indices inside each); check the seam, the
+    tail and a strided sample, with Payne-Hanek lanes on both sides of the seam."""
+    import torch
+
+    n = (1 << 30) + 4099
+    x = torch.empty(n, dtype=torch.float64, device=cuda)
+    fabe13.fill_uniform_device(x, 0xFABE1306, -1e5, 1e5)
+    seam = 1 << 30
+    probes = torch.tensor([0, 5, seam - 3, seam - 1, seam, seam + 1, seam + 4097, n - 1], device=cuda)
+    x[probes] = torch.tensor([1e300, -2.0 ** 45, 1e22, -1e200, 3e150, float("inf"), 1e18, -7e77], dtype=torch.float64, device=cuda)
+    s, c = fabe13.sincos(x)
+    torch.cuda.synchronize()
+    idx = torch.cat([torch.arange(0, 4096, device=cuda), torch.arange(seam - 4096, seam + 4099, device=cuda),
+                     torch.arange(0, n, 65537, device=cuda)])
+    xs = x[idx].cpu().numpy()
+    check_against_oracle(xs, s[idx].cpu().numpy(), c[idx].cpu().numpy(), None, oracle, label="two launch sequences")
+    hs, hc, _ = fabe13.host_core(xs, 0)
+    assert np.array_equal(bits(s[idx].cpu().numpy()), bits(hs)) and np.array_equal(bits(c[idx].cpu().numpy()), bits(hc))
+    worst = 0.0
+    for b in range(0, n, 1 << 27):
+        sl = slice(b, min(n, b + (1 << 27)))
+        v = (s[sl] * s[sl] + c[sl] * c[sl] - 1.0).abs()
+        worst = max(worst, torch.nan_to_num(v, nan=0.0).max().item())
+    assert worst <= 6e-16, worst
