@@ -34,7 +34,9 @@ def _stale():
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into lib/libfabe13.so.  Returns the path."""
+    """Compile csrc/*.cu for sm_100a into lib/libfabe13.so.  Returns the path.
+
+    FABE13_BUILD_DEFINES="A=1 B" in the environment adds -DA=1 -DB (used by tools/ for A/B builds of kernel variants)."""
     if not force and not _stale():
         return LIBPATH
     os.makedirs(LIBDIR, exist_ok=True)

@@ -9,7 +9,6 @@
 namespace fabe13 {
 
 struct LaunchTuning {
-    int threads;        // threads per block of the streaming kernel (multiple of 32)
     int blocks_per_sm;  // 0 = one tile per block (default); k > 0 = persistent grid of SMs * k blocks
     int tiles_per_block;  // consecutive tiles per block per grid-stride step
     int pdl;              // 1 = queue the launches of one call with programmatic dependent launch

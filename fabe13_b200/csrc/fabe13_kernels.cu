@@ -1,7 +1,7 @@
 // fabe13_kernels.cu -- sm_100a kernels for the FP64 array sincos path.
 //
 // Replaces the reference's SIMD array drivers fabe13_sincos_avx512 / _avx2 / _neon (fabe13/fabe13.c:545-614,
-// :469-541, :399-464) and their scalar tail loops (:339-358).  Three kernels:
+// :469-541, :399-464) and their scalar tail loops (:339-358).  Kernels:
 //
 //   sincos_stream_kernel      the hot path.  Grid-stride loop over tiles of 256*UNROLL 256-bit vectors, tiles taken
 //                             in address order (by default one tile per block, so DRAM sees one advancing window);
@@ -14,6 +14,8 @@
 //                             segment overflowed it also rescans the sin array for stashed arguments (a finite
 //                             value >= 2^45 can never be a sine) and reduces those in place.
 //   sincos_inline_kernel      small n: one launch, every path inline.
+//   zero_counters_kernel      clears the worklist header; first of the three launches of a large call, the other two
+//                             follow it with programmatic dependent launch.
 //
 // Data layout in HBM: three contiguous FP64 arrays (in, sin, cos), optional int64 k array (test hook), and a
 // workspace = { kSegments counters, 128 B apart } { kSegments x seg_cap u32 element indices }.

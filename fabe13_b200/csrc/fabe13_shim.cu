@@ -97,7 +97,6 @@ void load_env() {
 LaunchTuning current_tuning() {
     load_env();
     LaunchTuning t;
-    t.threads = 256;
     t.blocks_per_sm = (int)g_cfg.blocks_per_sm.load();
     t.tiles_per_block = (int)g_cfg.tiles_per_block.load();
     t.pdl = (int)g_cfg.pdl.load();
