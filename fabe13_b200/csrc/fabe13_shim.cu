@@ -31,6 +31,7 @@ using fabe13::LaunchTuning;
 constexpr int kMaxDevices = 64;
 constexpr int kSlots = 8;                                  // pipeline depth of the host path / max staging workers
 constexpr size_t kLaunchMaxElems = (size_t)1 << 30;        // per launch sequence; keeps 32-bit indices and alignment
+constexpr size_t kZeroCopyPageableMax = 32768;             // pageable callers: bounce through one small pinned block
 
 const uint64_t h_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
 
@@ -49,7 +50,7 @@ struct Config {
     std::atomic<long long> chunk_elems{(long long)1 << 22};
     std::atomic<long long> host_devices{1};
     std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, hardware threads / 2)
-    std::atomic<long long> zero_copy_max{32768};
+    std::atomic<long long> zero_copy_max{(long long)1 << 24};
 };
 
 Config g_cfg;
@@ -76,7 +77,7 @@ const OptionDesc kOptions[] = {
     {"chunk_elems", "FABE13_CUDA_CHUNK_ELEMS", &Config::chunk_elems, 1024, (long long)1 << 28},
     {"host_devices", "FABE13_CUDA_HOST_DEVICES", &Config::host_devices, 1, kMaxDevices},
     {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 0, kSlots},
-    {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 24},
+    {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 30},
 };
 
 void load_env() {
@@ -325,9 +326,9 @@ int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, 
     return 0;
 }
 
-// Small host-resident arrays: launch latency dominates, so skip the copy engines.  One kernel reads the pinned
-// host buffer over PCIe and writes both results straight back (zero-copy through the unified address space).
-// Pageable callers are bounced through a small pinned staging block.  Returns -1 if this route is not available
+// Small and medium host-resident arrays: skip the copy engines.  The kernels read the pinned host buffer over PCIe
+// and write both results straight back (zero-copy through the unified address space): no pipeline fill/drain, one
+// launch for small n.  Small pageable calls are bounced through a pinned staging block.  Returns -1 if this route is not available
 // (memory registered without a device mapping), in which case the caller takes the copy pipeline.
 int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned,
                const LaunchTuning& t, int core) {
@@ -339,7 +340,7 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
             if (s.small_stage) cudaFreeHost(s.small_stage);
             s.small_stage = nullptr;
             s.small_cap = 0;
-            const size_t cap = (size_t)g_cfg.zero_copy_max.load() > n ? (size_t)g_cfg.zero_copy_max.load() : n;
+            const size_t cap = kZeroCopyPageableMax > n ? kZeroCopyPageableMax : n;
             FABE13_TRY(cudaHostAlloc(&s.small_stage, 3 * cap * sizeof(double), cudaHostAllocDefault));
             s.small_cap = cap;
         }
@@ -356,11 +357,16 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
         return -1;
     }
     int launches = 0;
-    LaunchTuning ti = t;
-    ti.small_n = 1 << 30;  // always the single inline kernel here
-    cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, core, ti, s.info, nullptr,
+    void* ws = nullptr;
+    if (n >= (size_t)t.small_n)  // large enough for the streaming kernel: it needs its worklist scratch
+        FABE13_TRY(cudaMallocFromPoolAsync(&ws, fabe13::workspace_bytes(n, t), s.pool, s.small_stream));
+    cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, core, t, s.info, ws,
                                           s.small_stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
+    if (ws) {
+        cudaError_t e2 = cudaFreeAsync(ws, s.small_stream);
+        if (e == cudaSuccess) e = e2;
+    }
     if (e != cudaSuccess) return record(e, "launch_sincos(zero-copy)");
     FABE13_TRY(cudaStreamSynchronize(s.small_stream));
     if (!pinned) {
@@ -377,7 +383,10 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     std::lock_guard<std::mutex> lk(ds->pipe_mu);
     const LaunchTuning t = current_tuning();
     const int core = (int)g_cfg.core.load();
-    if (n <= (size_t)g_cfg.zero_copy_max.load()) {
+    // one kernel working on host memory directly: up to zero_copy_max elements for pinned arrays (faster than the
+    // copy pipeline up to ~1e7 elements, measured), small calls only for pageable ones (they need a bounce buffer)
+    const size_t zc_max = (size_t)g_cfg.zero_copy_max.load();
+    if (n <= (pinned ? zc_max : (zc_max < kZeroCopyPageableMax ? zc_max : kZeroCopyPageableMax))) {
         const int rc = host_small(*ds, in, sin_out, cos_out, n, pinned, t, core);
         if (rc >= 0) return rc;
     }

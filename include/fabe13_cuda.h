@@ -53,8 +53,9 @@ int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in,
 /* Host-pointer entry with a size_t length and an error return; fabe13_sincos() forwards here.
  * Pinned host memory (cudaHostAlloc / cudaHostRegister / fabe13_cuda_host_alloc) is copied directly by the copy
  * engines, H2D and D2H overlapped with the kernel chunk by chunk; pageable memory goes through pinned staging
- * buffers filled by worker threads.  Arrays of at most "zero_copy_max" elements skip the copy engines: one kernel
- * reads the pinned host buffer and writes the results back directly over PCIe.  With option "host_devices" > 1 the array is split into contiguous slices,
+ * buffers filled by worker threads.  Pinned arrays of at most "zero_copy_max" elements (default 2^24) skip the copy
+ * engines: the kernels read the host buffer and write the results back directly over PCIe (as do pageable calls of
+ * at most 32768 elements, through a bounce buffer).  With option "host_devices" > 1 the array is split into contiguous slices,
  * one per GPU. */
 int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n);
 
