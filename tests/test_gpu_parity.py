@@ -361,10 +361,13 @@ def test_host_pageable(fabe13, oracle, cuda, n):
     check_against_oracle(x, s, c, None, oracle, label=f"host pageable n={n}")
 
 
-@pytest.mark.parametrize("n", [10, 1_000_000, 30_000_001])
+@pytest.mark.parametrize("n", [10, 1_000_000, 6_000_001, 30_000_001])
 def test_host_pinned(fabe13, oracle, cuda, n):
+    """10 / 1e6: one zero-copy inline kernel; 6e6: zero-copy streaming kernel + second pass working on host memory;
+    3e7: the copy-engine pipeline.  Payne-Hanek lanes sprinkled in so the second pass runs on every route."""
     px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
     px.array[:] = oracle.fill_uniform(n, 70, -1e4, 1e4)
+    px.array[3::997] = oracle.fill_loguniform(len(px.array[3::997]), 71)
     fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)
     m = min(n, 2_000_000)
     check_against_oracle(px.array[:m], ps.array[:m], pc.array[:m], None, oracle, label="host pinned head")
