@@ -435,9 +435,14 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             memcpy(sl.h_in, in + off, m * sizeof(double));
             int rc = enqueue_chunk(*ds, sl, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core);
             if (rc == 0) {
-                cudaError_t e = cudaEventRecord(sl.done, sl.stream);
-                if (e == cudaSuccess) e = cudaEventSynchronize(sl.done);  // blocking event: the worker sleeps
-                if (e != cudaSuccess) rc = record(e, "cudaEventSynchronize(worker)");
+                cudaError_t e;
+                if (n >= ((size_t)1 << 22)) {  // long waits: sleep on a blocking event; short ones: spin (lower latency)
+                    e = cudaEventRecord(sl.done, sl.stream);
+                    if (e == cudaSuccess) e = cudaEventSynchronize(sl.done);
+                } else {
+                    e = cudaStreamSynchronize(sl.stream);
+                }
+                if (e != cudaSuccess) rc = record(e, "wait for chunk (worker)");
             }
             if (rc != 0) {
                 rc_all.store(rc);
