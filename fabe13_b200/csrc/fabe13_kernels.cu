@@ -193,14 +193,15 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
                     }
                 }
             }
-            if (__any_sync(0xFFFFFFFFu, !all_plain)) {  // rare: some lane is tiny, special or in the Payne-Hanek range
+            // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
+            if (__ballot_sync(0xFFFFFFFFu, !all_plain) != 0) {  // rare: tiny, special or Payne-Hanek-range lanes
                 uint32_t n_huge = 0;
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
                 }
-                if (__any_sync(0xFFFFFFFFu, n_huge != 0)) {  // compact the Payne-Hanek lanes of this warp
+                if (__ballot_sync(0xFFFFFFFFu, n_huge != 0) != 0) {  // compact the Payne-Hanek lanes of this warp
                     worklist_push(n_huge, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
 #pragma unroll
                         for (int u = 0; u < UNROLL; ++u) {
