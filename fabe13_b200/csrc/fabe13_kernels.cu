@@ -29,7 +29,10 @@
 namespace fabe13 {
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef FABE13_BLOCK_THREADS
+#define FABE13_BLOCK_THREADS 256
+#endif
+constexpr int kThreads = FABE13_BLOCK_THREADS;
 // Worklist segments: blocks append to segment blockIdx % kSegments, so same-address atomics (which serialise in
 // L2) are spread over kSegments counters placed one 128-byte line apart.
 constexpr int kSegments = 32;

@@ -699,3 +699,20 @@ def test_more_than_one_launch_sequence(fabe13, cuda, oracle):
         v = (s[sl] * s[sl] + c[sl] * c[sl] - 1.0).abs()
         worst = max(worst, torch.nan_to_num(v, nan=0.0).max().item())
     assert worst <= 6e-16, worst
+
+
+@pytest.mark.parametrize("small_n", [0, 1 << 30])
+def test_random_bit_patterns(fabe13, cuda, oracle, small_n):
+    """Fuzz over the whole binary64 space (uniform random bit patterns: ~half of them in the Payne-Hanek range, NaNs
+    with payloads, subnormals, both zeros): the device agrees with the host instantiation bit for bit, with libm to
+    4.5e-16 on every finite input, and NaN/Inf canonicalise."""
+    fabe13.set_option("small_n", small_n)
+    rng = np.random.default_rng(20261019)
+    x = rng.integers(0, 1 << 64, size=3_000_003, dtype=np.uint64).view(np.float64)
+    s, c, k = gpu_sincos_k(fabe13, cuda, x)
+    hs, hc, hk = fabe13.host_core(x, 0)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc)) and np.array_equal(k, hk)
+    fin = np.isfinite(x)
+    ls, lc = oracle.libm(x[fin])
+    assert max(np.abs(s[fin] - ls).max(), np.abs(c[fin] - lc).max()) <= QUALITY_TOL
+    assert np.all(bits(s)[~fin] == QNAN) and np.all(bits(c)[~fin] == QNAN)

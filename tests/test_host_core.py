@@ -111,3 +111,17 @@ def test_against_mpmath_truth(fabe13, oracle):
             xm = mp.mpf(float(x))
             assert abs(mp.mpf(float(si)) - mp.sin(xm)) <= tol, (x, si)
             assert abs(mp.mpf(float(ci)) - mp.cos(xm)) <= tol, (x, ci)
+
+
+def test_random_bit_patterns_host(fabe13, oracle):
+    """Same fuzz as the GPU test, on the host instantiation (runs in CPU-only CI)."""
+    rng = np.random.default_rng(20261019)
+    x = rng.integers(0, 1 << 64, size=500_000, dtype=np.uint64).view(np.float64)
+    for core in (0, 1):
+        s, c, k = fabe13.host_core(x, core)
+        fin = np.isfinite(x)
+        ls, lc = oracle.libm(x[fin])
+        assert max(np.abs(s[fin] - ls).max(), np.abs(c[fin] - lc).max()) <= QUALITY_TOL
+        assert np.all(bits(s)[~fin] == np.uint64(0x7FF8000000000000)) and np.all(bits(c)[~fin] == np.uint64(0x7FF8000000000000))
+        tiny = fin & (np.abs(x) <= 2.0 ** -27)
+        assert np.array_equal(bits(s)[tiny], bits(x)[tiny]) and np.all(c[tiny] == 1.0)
