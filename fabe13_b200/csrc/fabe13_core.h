@@ -148,9 +148,9 @@ FABE13_HD double fabe13_cody_waite(double x, double k) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // 2b. Payne-Hanek for |x| >= 2^45 (works for any normal |x| >= 2^-10).
-//     |x| = m * 2^e with the 53-bit integer mantissa m.  2/pi = sum_j W[j] 2^(-64 j).  Words whose product with
-//     m*2^e is a multiple of 4 cannot change (k mod 4, fraction) and are skipped; the next four words give the
-//     integer bits mod 4 and >= 126 fraction bits (the closest a double gets to a multiple of pi/2 costs ~62).
+//     |x| = m * 2^e with the 53-bit integer mantissa m.  2/pi = sum_j W[j] 2^(-64 j).  Bits whose product with
+//     m*2^e is a multiple of 4 cannot change (k mod 4, fraction) and are skipped; the next 192 bits give the
+//     integer bits mod 4 and 126 usable fraction bits (the closest a double gets to a multiple of pi/2 costs ~62).
 //     Returns q = rint(|x|*2/pi) mod 4 and r = |x| - rint(|x|*2/pi)*pi/2, |r| <= pi/4, to < 1 ulp.
 // ---------------------------------------------------------------------------------------------------------------
 FABE13_HD void fabe13_mul_64x64(uint64_t a, uint64_t b, uint64_t* hi, uint64_t* lo) {
@@ -180,35 +180,64 @@ FABE13_HD double fabe13_u64_to_double(uint64_t v) {  // exact for v < 2^53
 #endif
 }
 
+FABE13_HD uint64_t fabe13_funnel_left(uint64_t hi, uint64_t lo, int o) {  // top 64 bits of (hi:lo) << o, 0 <= o <= 63
+#if defined(__CUDA_ARCH__)
+    // two native 32-bit funnel shifts after picking the three source words by o >= 32
+    const uint32_t a3 = (uint32_t)(hi >> 32), a2 = (uint32_t)hi, a1 = (uint32_t)(lo >> 32), a0 = (uint32_t)lo;
+    const bool big = o >= 32;
+    const uint32_t x2 = big ? a2 : a3, x1 = big ? a1 : a2, x0 = big ? a0 : a1;
+    return ((uint64_t)__funnelshift_l(x1, x2, (unsigned)o) << 32) | __funnelshift_l(x0, x1, (unsigned)o);  // shift taken mod 32
+#else
+    return (hi << o) | ((lo >> 1) >> (63 - o));
+#endif
+}
+
+// The 192-bit window of 2/pi that starts at global bit g0 of the table (bit 0 = MSB of W[0]), as three 64-bit words.
+FABE13_HD void fabe13_two_over_pi_window(const uint64_t* W, int g0, uint64_t* v2, uint64_t* v1, uint64_t* v0) {
+#if defined(__CUDA_ARCH__)
+    // 32-bit view of the table: stream word s is the high half of W[s/2] for even s (little-endian: index s^1);
+    // seven loads, six native funnel shifts
+    const uint32_t* W32 = reinterpret_cast<const uint32_t*>(W);
+    const int s = g0 >> 5;
+    const unsigned o = (unsigned)g0 & 31u;
+    uint32_t a[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) a[i] = W32[(s + i) ^ 1];
+    *v2 = ((uint64_t)__funnelshift_l(a[1], a[0], o) << 32) | __funnelshift_l(a[2], a[1], o);
+    *v1 = ((uint64_t)__funnelshift_l(a[3], a[2], o) << 32) | __funnelshift_l(a[4], a[3], o);
+    *v0 = ((uint64_t)__funnelshift_l(a[5], a[4], o) << 32) | __funnelshift_l(a[6], a[5], o);
+#else
+    const int jw = g0 >> 6, o = g0 & 63;
+    const uint64_t t0 = W[jw], t1 = W[jw + 1], t2 = W[jw + 2], t3 = W[jw + 3];
+    *v2 = fabe13_funnel_left(t0, t1, o);
+    *v1 = fabe13_funnel_left(t1, t2, o);
+    *v0 = fabe13_funnel_left(t2, t3, o);
+#endif
+}
+
 FABE13_HD double fabe13_payne_hanek(uint64_t abs_bits, const uint64_t* W, int* q_out) {
     const int e = (int)(abs_bits >> 52) - 1075;  // |x| = m * 2^e
     const uint64_t m = (abs_bits & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
-    const int j0 = ((e - 2) >> 6) + 1;  // first word whose product is not a multiple of 4
-    const int s0 = e - 64 * j0;         // scale of that word: in [-62, 1]
-    const uint64_t w0 = W[j0], w1 = W[j0 + 1], w2 = W[j0 + 2], w3 = W[j0 + 3];
+    // Bit i of 2/pi (weight 2^-i) contributes m*2^(e-i): a multiple of 4 for i <= e-2.  Take the 192 bits from
+    // i = e-1 on, bit-aligned out of four table words (W[0] is the zero integer part, so bit i sits at global
+    // position i+63).  Then x*2/pi = m*V*2^-190 (mod 4), up to a tail below 2^-138.
+    uint64_t v2, v1, v0;
+    fabe13_two_over_pi_window(W, e + 62, &v2, &v1, &v0);
 
-    // low 256 bits of m * (w0:w1:w2:w3), top three words only (the lowest contributes just its carry)
-    uint64_t hi3, lo3, hi2, lo2, hi1, lo1, hi0, lo0;
-    fabe13_mul_64x64(m, w3, &hi3, &lo3);
-    fabe13_mul_64x64(m, w2, &hi2, &lo2);
-    fabe13_mul_64x64(m, w1, &hi1, &lo1);
-    fabe13_mul_64x64(m, w0, &hi0, &lo0);
-    (void)lo3;
-    (void)hi0;
-    const uint64_t R1 = lo2 + hi3;
-    const uint64_t c1 = (R1 < lo2) ? 1u : 0u;
-    const uint64_t R2 = lo1 + (hi2 + c1);  // hi2 < 2^53: no overflow in the inner sum
-    const uint64_t c2 = (R2 < lo1) ? 1u : 0u;
-    const uint64_t R3 = lo0 + (hi1 + c2);
+    // low 192 bits of m*(v2:v1:v0): bits [191:190] = k mod 4, bits [189:0] the fraction (the lowest word only
+    // matters through its carry, and its own bits are below what a double can use)
+    uint64_t h0, l0, h1, l1, h2, l2;
+    fabe13_mul_64x64(m, v0, &h0, &l0);
+    fabe13_mul_64x64(m, v1, &h1, &l1);
+    fabe13_mul_64x64(m, v2, &h2, &l2);
+    (void)l0;
+    (void)h2;
+    const uint64_t P1 = l1 + h0;
+    const uint64_t P2 = l2 + h1 + ((P1 < l1) ? 1u : 0u);
 
-    // binary point sits at bit 192 - s0 of R3:R2:R1:R0; shift left so it lands between bits 62 and 61 of A2
-    const int L = 62 + s0;  // 0..63
-    const uint64_t A2 = (R3 << L) | ((R2 >> 1) >> (63 - L));
-    const uint64_t A1 = (R2 << L) | ((R1 >> 1) >> (63 - L));
-
-    unsigned q = (unsigned)(A2 >> 62);
-    uint64_t f_hi = (A2 << 2) | (A1 >> 62);  // fraction, scale 2^-128
-    uint64_t f_lo = A1 << 2;
+    unsigned q = (unsigned)(P2 >> 62);
+    uint64_t f_hi = (P2 << 2) | (P1 >> 62);  // fraction, scale 2^-128
+    uint64_t f_lo = P1 << 2;
 
     // round to nearest: fraction >= 1/2 -> next integer, negative remainder
     const uint64_t neg = f_hi >> 63;
@@ -217,28 +246,21 @@ FABE13_HD double fabe13_payne_hanek(uint64_t abs_bits, const uint64_t* W, int* q
     f_lo = (f_lo ^ flip) + neg;
     f_hi = (f_hi ^ flip) + ((neg != 0 && f_lo == 0) ? 1u : 0u);
 
-    int lead = 0;
-    if (f_hi == 0) {  // > 64 bits of cancellation: never for doubles (worst case ~62), kept for safety
-        f_hi = f_lo;
-        f_lo = 0;
-        lead = 64;
-    }
-    double r = 0.0;
-    if (f_hi != 0) {
-        const int lz = fabe13_clz64(f_hi);
-        const uint64_t mant = (f_hi << lz) | ((f_lo >> 1) >> (63 - lz));  // top bit set
-        lead += lz;
-        // |fraction| = mant * 2^(-64 - lead); split into an exact 53-bit head and 11-bit tail
-        const double scale = fabe13_from_bits((uint64_t)(1023 - 64 - lead) << 52);
-        const double f_head = FABE13_MUL(fabe13_u64_to_double(mant & ~0x7FFull), scale);
-        const double f_tail = FABE13_MUL(fabe13_u64_to_double(mant & 0x7FFull), scale);
-        // times pi/2 in double-double
-        const double p = FABE13_MUL(f_head, FABE13_PH_PIO2_HI);
-        double t = FABE13_FMA(f_head, FABE13_PH_PIO2_HI, -p);
-        t = FABE13_FMA(f_head, FABE13_PH_PIO2_LO, t);
-        t = FABE13_FMA(f_tail, FABE13_PH_PIO2_HI, t);
-        r = FABE13_ADD(p, t);
-    }
+    // Normalise.  No double comes closer to a multiple of pi/2 than 2^-61.x of a quadrant (the worst case is
+    // 6381956970095103 * 2^797, checked in the tests), so the top 64 fraction bits are never all zero; "| 1" only
+    // keeps clz defined.
+    const int lead = fabe13_clz64(f_hi | 1u);
+    const uint64_t mant = fabe13_funnel_left(f_hi, f_lo, lead);  // top bit set
+    // |fraction| = mant * 2^(-64 - lead): an exact 53-bit head assembled bit by bit (1.f * 2^(-1-lead)) and an
+    // 11-bit tail
+    const double f_head = fabe13_from_bits(((uint64_t)(1022 - lead) << 52) | ((mant >> 11) & 0x000FFFFFFFFFFFFFull));
+    const double f_tail = FABE13_MUL(fabe13_u64_to_double(mant & 0x7FFull), fabe13_from_bits((uint64_t)(1023 - 64 - lead) << 52));
+    // times pi/2 in double-double
+    const double p = FABE13_MUL(f_head, FABE13_PH_PIO2_HI);
+    double t = FABE13_FMA(f_head, FABE13_PH_PIO2_HI, -p);
+    t = FABE13_FMA(f_head, FABE13_PH_PIO2_LO, t);
+    t = FABE13_FMA(f_tail, FABE13_PH_PIO2_HI, t);
+    const double r = FABE13_ADD(p, t);
     *q_out = (int)(q & 3u);
     return neg ? -r : r;
 }
