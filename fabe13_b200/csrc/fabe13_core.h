@@ -349,15 +349,21 @@ FABE13_HD bool fabe13_is_plain(uint32_t ahi) {
 // complete fix-up used wherever the reduction already handled every range.
 enum { FABE13_STASH_NONE = 0, FABE13_STASH_SIN = 1, FABE13_STASH_COS = 2 };
 
-template <int STASH>
-FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, uint32_t q, uint64_t* s_bits, uint64_t* c_bits) {
+// quadrant rotation on bit patterns: q = 0 -> (s, c), 1 -> (c, -s), 2 -> (-s, -c), 3 -> (-c, s)
+FABE13_HD void fabe13_rotate(double sin_r, double cos_r, uint32_t q, uint64_t* s_bits, uint64_t* c_bits) {
     const uint64_t sb = fabe13_bits(sin_r);
     const uint64_t cb = fabe13_bits(cos_r);
     const bool swap = (q & 1u) != 0;
-    uint64_t so = swap ? cb : sb;  // q: 0 -> ( s,  c)  1 -> ( c, -s)  2 -> (-s, -c)  3 -> (-c,  s)
-    uint64_t co = swap ? sb : cb;
-    so ^= (uint64_t)(q & 2u) << 62;
-    co ^= (uint64_t)((q + 1u) & 2u) << 62;
+    const uint64_t so = swap ? cb : sb;
+    const uint64_t co = swap ? sb : cb;
+    *s_bits = so ^ ((uint64_t)(q & 2u) << 62);
+    *c_bits = co ^ ((uint64_t)((q + 1u) & 2u) << 62);
+}
+
+template <int STASH>
+FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, uint32_t q, uint64_t* s_bits, uint64_t* c_bits) {
+    uint64_t so, co;
+    fabe13_rotate(sin_r, cos_r, q, &so, &co);
     // overrides, merged into one select per output: tiny -> (x, 1); NaN/Inf -> (qNaN, qNaN); [stash -> x]
     const uint32_t ahi = fabe13_abs_hi(x_bits);
     const bool special = fabe13_is_special(ahi);
@@ -365,10 +371,24 @@ FABE13_HD void fabe13_fixup(uint64_t x_bits, double sin_r, double cos_r, uint32_
     const uint64_t alt_s = special ? FABE13_QNAN_BITS : x_bits;
     uint64_t alt_c = special ? FABE13_QNAN_BITS : FABE13_ONE_BITS;
     if (STASH == FABE13_STASH_COS) alt_c = fabe13_is_huge(ahi) ? x_bits : alt_c;
-    so = override_ ? alt_s : so;
-    co = override_ ? alt_c : co;
-    *s_bits = so;
-    *c_bits = co;
+    *s_bits = override_ ? alt_s : so;
+    *c_bits = override_ ? alt_c : co;
+}
+
+// An element known to be in the Payne-Hanek range (2^45 <= |x| < Inf): reduction, core, rotation -- no overrides
+// can apply.  Returns q = k mod 4 (what the k hook reports for such elements).
+template <int CORE>
+FABE13_HD int fabe13_sincos_huge(uint64_t x_bits, const uint64_t* ph_table, uint64_t* s_bits, uint64_t* c_bits) {
+    int qa;
+    double r = fabe13_payne_hanek(x_bits & FABE13_ABS_MASK, ph_table, &qa);
+    if (x_bits >> 63) {  // odd symmetry: k(-x) = -k(x), r(-x) = -r(x)
+        r = -r;
+        qa = (4 - qa) & 3;
+    }
+    double sr, cr;
+    fabe13_core<CORE>(r, &sr, &cr);
+    fabe13_rotate(sr, cr, (uint32_t)qa, s_bits, c_bits);
+    return qa;
 }
 
 // One element, every path inline (used by the host scalar API, by small-N and edge elements on the device and
@@ -377,30 +397,18 @@ template <int CORE>
 FABE13_HD void fabe13_sincos_one(uint64_t x_bits, const uint64_t* ph_table, uint64_t* s_bits, uint64_t* c_bits,
                                  int64_t* k_out) {
     const uint32_t ahi = fabe13_abs_hi(x_bits);
-    double r;
-    uint32_t q;
-    int64_t k;
     if (fabe13_is_huge(ahi)) {
-        int qa;
-        r = fabe13_payne_hanek(x_bits & FABE13_ABS_MASK, ph_table, &qa);
-        if (x_bits >> 63) {  // odd symmetry: k(-x) = -k(x), r(-x) = -r(x)
-            r = -r;
-            qa = (4 - qa) & 3;
-        }
-        q = (uint32_t)qa;
-        k = qa;
-    } else {
-        const double x = fabe13_from_bits(x_bits);
-        double biased;
-        const double kd = fabe13_quadrant_index(x, &biased);
-        r = fabe13_cody_waite(x, kd);
-        q = fabe13_q_from_biased(biased);
-        k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
+        *k_out = fabe13_sincos_huge<CORE>(x_bits, ph_table, s_bits, c_bits);
+        return;
     }
+    const double x = fabe13_from_bits(x_bits);
+    double biased;
+    const double kd = fabe13_quadrant_index(x, &biased);
+    const double r = fabe13_cody_waite(x, kd);
     double sr, cr;
     fabe13_core<CORE>(r, &sr, &cr);
-    fabe13_fixup<FABE13_STASH_NONE>(x_bits, sr, cr, q, s_bits, c_bits);
-    *k_out = k;
+    fabe13_fixup<FABE13_STASH_NONE>(x_bits, sr, cr, fabe13_q_from_biased(biased), s_bits, c_bits);
+    *k_out = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
 }
 
 #endif  // FABE13_CORE_H

@@ -255,11 +255,10 @@ struct SecondPassArgs {
 template <int CORE>
 __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t idx, uint64_t xb, const uint64_t* table) {
     uint64_t sb, cb;
-    int64_t k;
-    fabe13_sincos_one<CORE>(xb, table, &sb, &cb, &k);
+    const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);  // the caller has checked is_stashed(xb)
     if (a.sin_out) a.sin_out[idx] = __longlong_as_double((long long)sb);
     if (a.cos_out) a.cos_out[idx] = __longlong_as_double((long long)cb);
-    if (a.k_out) a.k_out[idx] = k;
+    if (a.k_out) a.k_out[idx] = q;
 }
 
 __device__ __forceinline__ void stage_table(uint64_t* table) {
