@@ -312,7 +312,7 @@ def run_cuda_arm(args):
     import torch
     import torch.distributed as dist
 
-    import fabe13_b200 as fb
+    import fabe_b200 as fb
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,6 +1,6 @@
-"""fabe13_b200 -- B200-native (sm_100a) FP64 array sincos behind the FABE13 C API.
+"""fabe_b200 -- B200-native (sm_100a) FP64 array sincos behind the FABE13 C API.
 
-The product is libfabe13.so (fabe13_b200/lib/, built from fabe13_b200/csrc/ by fabe13_b200/build.py); this package
+The product is libfabe13.so (fabe_b200/lib/, built from fabe_b200/csrc/ by fabe_b200/build.py); this package
 is its ctypes binding.  See DESIGN.md and INTEGRATION.md.
 """
 from ._lib import Fabe13Error  # noqa: F401

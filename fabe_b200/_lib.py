@@ -1,6 +1,6 @@
 """ctypes binding of libfabe13.so (the C ABI declared in include/fabe13.h and include/fabe13_cuda.h).
 
-There is no Python or CPU fallback: if the shared library has not been built (python -m fabe13_b200.build, or
+There is no Python or CPU fallback: if the shared library has not been built (python -m fabe_b200.build, or
 __graft_entry__.build()) importing the binding raises.
 """
 import ctypes
@@ -63,7 +63,7 @@ def load():
     if _lib is None:
         if not os.path.exists(LIBPATH):
             raise ImportError(
-                f"{LIBPATH} is missing: build it with `python -m fabe13_b200.build` "
+                f"{LIBPATH} is missing: build it with `python -m fabe_b200.build` "
                 "(there is no fallback implementation)"
             )
         lib = ctypes.CDLL(LIBPATH)

@@ -1,7 +1,7 @@
 """Build libfabe13.so (the C-ABI library with the sm_100a kernels) in-tree with nvcc.
 
-The .so lands in fabe13_b200/lib/ so that it travels with the repository snapshot to the GPU box; nothing is
-JIT-compiled at import time.  `python -m fabe13_b200.build` rebuilds it.
+The .so lands in fabe_b200/lib/ so that it travels with the repository snapshot to the GPU box; nothing is
+JIT-compiled at import time.  `python -m fabe_b200.build` rebuilds it.
 """
 import os
 import shutil

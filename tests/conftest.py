@@ -42,12 +42,12 @@ def golden():
 @pytest.fixture(scope="session")
 def fabe13():
     """The product binding; building the library is part of the test session (nvcc cross-compiles without a GPU)."""
-    from fabe13_b200.build import build_library
+    from fabe_b200.build import build_library
 
     build_library()
-    import fabe13_b200
+    import fabe_b200
 
-    return fabe13_b200
+    return fabe_b200
 
 
 @pytest.fixture(scope="session")

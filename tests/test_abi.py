@@ -23,7 +23,7 @@ def declared_functions(header):
 
 
 def test_library_exports_every_declared_symbol(fabe13):
-    from fabe13_b200 import _lib
+    from fabe_b200 import _lib
 
     lib = _lib.load()
     names = declared_functions("fabe13.h") + declared_functions("fabe13_cuda.h")
@@ -52,7 +52,7 @@ def test_reference_programs_compile_against_our_header(tmp_path):
         " (void)in;(void)s;(void)c; return 0;}\n"
     )
     exe = tmp_path / "user"
-    libdir = os.path.join(ROOT, "fabe13_b200", "lib")
+    libdir = os.path.join(ROOT, "fabe_b200", "lib")
     import subprocess
 
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,

@@ -593,7 +593,7 @@ def test_torch_ops_registration(fabe13, cuda, oracle):
     """torch.ops.fabe13.sincos / sin / cos on CUDA and CPU tensors, incl. a non-contiguous view."""
     import torch
 
-    import fabe13_b200.torch_ops  # noqa: F401  (registers the operators)
+    import fabe_b200.torch_ops  # noqa: F401  (registers the operators)
 
     x = oracle.fill_uniform(300_000, 501, -1e5, 1e5).reshape(300, 1000)
     hs, hc, _ = fabe13.host_core(x.ravel(), 0)

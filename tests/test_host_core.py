@@ -1,4 +1,4 @@
-"""The per-element algorithm (fabe13_b200/csrc/fabe13_core.h) is one piece of code compiled for the device and for
+"""The per-element algorithm (fabe_b200/csrc/fabe13_core.h) is one piece of code compiled for the device and for
 the host.  These tests run its HOST instantiation (the implementation of the scalar API, reached in bulk through the
 fabe13_debug_host_core test hook) against the oracle, the golden vectors and exact quadrants -- so the algorithm is
 checked on every commit even where no GPU exists.  The `-m gpu` tests then check the device instantiation."""

@@ -18,13 +18,13 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    import fabe13_b200
+    import fabe_b200
     from oracle.loader import Oracle
 
-    b, e = fabe13_b200.shard_bounds(N, world, rank)
+    b, e = fabe_b200.shard_bounds(N, world, rank)
     o = Oracle()
     x = o.fill_uniform(e - b, 0xFABE1303, -1e4, 1e4, first_index=b)  # the slice of the global array this rank owns
-    s, c, _ = fabe13_b200.host_core(x)  # host instantiation of the core (no GPU here)
+    s, c, _ = fabe_b200.host_core(x)  # host instantiation of the core (no GPU here)
     # every rank reports (begin, end, checksum, elapsed); elapsed is reduced with MAX exactly as bench.py does
     info = torch.tensor([b, e], dtype=torch.int64)
     gathered = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
@@ -40,7 +40,7 @@ def _worker(rank, world, port, q):
 
 
 def test_two_rank_sharding_gloo():
-    from fabe13_b200.build import build_library
+    from fabe_b200.build import build_library
 
     build_library()
     world = 2
@@ -59,9 +59,9 @@ def test_two_rank_sharding_gloo():
     assert tmax == 1.5  # max over ranks
     # the sharded run reproduces the single-process result
     sys.path.insert(0, ROOT)
-    import fabe13_b200
+    import fabe_b200
     from oracle.loader import Oracle
 
     x = Oracle().fill_uniform(N, 0xFABE1303, -1e4, 1e4)
-    s, c, _ = fabe13_b200.host_core(x)
+    s, c, _ = fabe_b200.host_core(x)
     assert abs(chk - float(np.abs(s).sum() + np.abs(c).sum())) < 1e-6

@@ -1,5 +1,5 @@
 // abi_bench.cu -- latency / throughput of the C ABI entry points measured from C (no Python in the loop).
-//   nvcc -O2 -o tools/abi_bench tools/abi_bench.cu -Iinclude -Lfabe13_b200/lib -lfabe13 -Xlinker -rpath -Xlinker '$ORIGIN/../fabe13_b200/lib'
+//   nvcc -O2 -o tools/abi_bench tools/abi_bench.cu -Iinclude -Lfabe_b200/lib -lfabe13 -Xlinker -rpath -Xlinker '$ORIGIN/../fabe_b200/lib'
 // Prints, per n: wall time of fabe13_sincos_device + stream sync, GPU time between events, and the host-pointer
 // entry (pinned and pageable) wall time.
 #include <cuda_runtime.h>

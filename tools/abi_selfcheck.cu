@@ -1,7 +1,7 @@
 // abi_selfcheck.cu -- C-level self check of the array entry points (compute-sanitizer is closed on the GPU pool, so
 // memory safety is probed the manual way: guard words around every output, every alignment offset, every kernel path,
 // and a bit-for-bit comparison with the host instantiation of the core).
-//   nvcc -O1 -std=c++17 -o tools/abi_selfcheck tools/abi_selfcheck.cu -Iinclude -Lfabe13_b200/lib -lfabe13 -Xlinker -rpath -Xlinker '$ORIGIN/../fabe13_b200/lib'
+//   nvcc -O1 -std=c++17 -o tools/abi_selfcheck tools/abi_selfcheck.cu -Iinclude -Lfabe_b200/lib -lfabe13 -Xlinker -rpath -Xlinker '$ORIGIN/../fabe_b200/lib'
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>

@@ -11,7 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import fabe13_b200 as fb  # noqa: E402
+import fabe_b200 as fb  # noqa: E402
 from oracle.loader import Oracle, Reference, ref_variant  # noqa: E402
 
 

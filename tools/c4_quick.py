@@ -3,7 +3,7 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import fabe13_b200 as fb
+import fabe_b200 as fb
 from tools.sweep import report, time_steps
 tag = sys.argv[1] if len(sys.argv) > 1 else ""
 dev = torch.device("cuda:0")

@@ -4,7 +4,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-import fabe13_b200 as fb
+import fabe_b200 as fb
 n = 250_000_000
 px, ps, pc = fb.PinnedArray(n), fb.PinnedArray(n), fb.PinnedArray(n)
 px.array[:] = np.linspace(-1e4, 1e4, n)

@@ -17,7 +17,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import fabe13_b200 as fb  # noqa: E402
+import fabe_b200 as fb  # noqa: E402
 
 
 def fmt_n(n):

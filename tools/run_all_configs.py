@@ -19,7 +19,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import fabe13_b200 as fb  # noqa: E402
+import fabe_b200 as fb  # noqa: E402
 from oracle.loader import Oracle, Reference, cpu_model, ref_variant  # noqa: E402
 from parity import check_against_oracle  # noqa: E402
 

@@ -3,7 +3,7 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import fabe13_b200 as fb
+import fabe_b200 as fb
 from tools.sweep import report, time_steps
 dev = torch.device("cuda:0")
 n = 1_000_000_000
