@@ -61,12 +61,13 @@ def load():
     """Load libfabe13.so once; raise loudly if it is missing or does not export the declared ABI."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIBPATH):
+        path = os.environ.get("FABE13_LIBRARY") or LIBPATH  # override: A/B builds of kernel variants (tools/)
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIBPATH} is missing: build it with `python -m fabe_b200.build` "
+                f"{path} is missing: build it with `python -m fabe_b200.build` "
                 "(there is no fallback implementation)"
             )
-        lib = ctypes.CDLL(LIBPATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in signatures().items():
             fn = getattr(lib, name)  # AttributeError = the .so does not export what the headers declare
             fn.restype = res

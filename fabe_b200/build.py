@@ -33,13 +33,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into lib/libfabe13.so.  Returns the path.
+def build_library(force=False, verbose=False, out=None):
+    """Compile csrc/*.cu for sm_100a into lib/libfabe13.so (or `out`).  Returns the path.
 
-    FABE13_BUILD_DEFINES="A=1 B" in the environment adds -DA=1 -DB (used by tools/ for A/B builds of kernel variants)."""
-    if not force and not _stale():
+    FABE13_BUILD_DEFINES="A=1 B" in the environment adds -DA=1 -DB (used by tools/ for A/B builds of kernel variants;
+    pair it with `out` and load the result through FABE13_LIBRARY)."""
+    if out is None and not force and not _stale():
         return LIBPATH
     os.makedirs(LIBDIR, exist_ok=True)
+    target = out or LIBPATH
+    if out:
+        os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     cmd = [
         _nvcc(),
         "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,7 +53,7 @@ def build_library(force=False, verbose=False):
         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-mfma,-fvisibility=hidden",
         "-Xptxas", "-v" if verbose else "-O3",
     ] + [f"-D{d}" for d in os.environ.get("FABE13_BUILD_DEFINES", "").split() if d] + [
-        "-o", LIBPATH,
+        "-o", target,
     ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -57,8 +61,9 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libfabe13.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIBPATH
+    return target
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose="-v" in sys.argv))
+    outs = [a for a in sys.argv[1:] if not a.startswith("-")]
+    print(build_library(force=True, verbose="-v" in sys.argv, out=outs[0] if outs else None))

@@ -9,6 +9,10 @@
 namespace fabe13 {
 
 struct LaunchTuning {
+    int worklist;       // Payne-Hanek worklist: 0 = by size (local below hybrid_min_n, hybrid from there on);
+                        // 1 = global list + second-pass kernel; 2 = warp-local lists in shared memory, one launch,
+                        // no scratch; 3 = hybrid (local for warps with >= 4 such lanes, global for stragglers)
+    int hybrid_min_n;   // worklist = 0: arrays of at least this many elements take the hybrid sequence
     int blocks_per_sm;  // 0 = one tile per block (default); k > 0 = persistent grid of SMs * k blocks
     int tiles_per_block;  // consecutive tiles per block per grid-stride step
     int pdl;              // 1 = queue the launches of one call with programmatic dependent launch
@@ -23,7 +27,8 @@ struct DeviceInfo {
     int sm_count;
 };
 
-// Bytes of scratch a launch over n elements needs for its Payne-Hanek worklist (header + entries).
+// Bytes of scratch a launch over n elements needs for its Payne-Hanek worklist (header + entries); 0 when the
+// launch keeps its worklists in shared memory.
 size_t workspace_bytes(size_t n, const LaunchTuning& t);
 
 // Enqueue the sincos path for n <= 2^31 elements on `stream`.  `workspace` must hold workspace_bytes(n) bytes

@@ -3,7 +3,12 @@
 // Replaces the reference's SIMD array drivers fabe13_sincos_avx512 / _avx2 / _neon (fabe13/fabe13.c:545-614,
 // :469-541, :399-464) and their scalar tail loops (:339-358).  Kernels:
 //
-//   sincos_stream_kernel      the hot path.  Grid-stride loop over tiles of 256*UNROLL 256-bit vectors, tiles taken
+//   sincos_fused_kernel       the hot path (default).  Same streaming loop as sincos_stream_kernel below, but the
+//                             Payne-Hanek lanes of a tile are compacted into a worklist in the block's SHARED memory
+//                             and reduced by the same block in a second pass over that list (dense warps), right
+//                             after the tile's vector stores: one launch per call, no scratch in HBM, and the 8-byte
+//                             result stores of the second pass merge in L2 with the lines the block has just written.
+//   sincos_stream_kernel      option worklist=1.  Grid-stride loop over tiles of 256*UNROLL 256-bit vectors, tiles taken
 //                             in address order (by default one tile per block, so DRAM sees one advancing window);
 //                             each thread issues LDG.E.NA.256 for its vectors, then two STG.E.EF.256 per vector.
 //                             Per lane: reference-exact k, Cody-Waite, polynomial/Psi core, integer-pipe fix-up.
@@ -33,6 +38,10 @@ namespace {
 #define FABE13_BLOCK_THREADS 256
 #endif
 constexpr int kThreads = FABE13_BLOCK_THREADS;
+// resident blocks per SM the fused kernel is compiled for (register cap 65536 / (256 * 6) -> 40)
+#ifndef FABE13_FUSED_MIN_BLOCKS
+#define FABE13_FUSED_MIN_BLOCKS 6
+#endif
 // Worklist segments: blocks append to segment blockIdx % kSegments, so same-address atomics (which serialise in
 // L2) are spread over kSegments counters placed one 128-byte line apart.
 constexpr int kSegments = 32;
@@ -244,6 +253,165 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
     }
 }
 
+
+// ---- the default hot path: streaming tile + warp-local worklist (+ global worklist for stragglers) --------------
+// Phase 1 is the streaming tile of sincos_stream_kernel: every lane runs the fast path and the vectors are stored
+// (a Payne-Hanek lane parks x itself in its output slot).  One warp ballot per tile says whether any lane was not
+// plain; only then (rare for ordinary data) the warp counts its Payne-Hanek lanes and
+//   * count >= kLocalMin: compacts (x, offset-in-tile) pairs into its own slice of shared memory and strides over
+//     that list with all lanes busy -- Payne-Hanek reduction, core, rotation, two 8-byte stores that merge in L2
+//     with the lines the warp has just written.  No block-wide barrier, no scratch in HBM, cost proportional to
+//     the number of such lanes (rounded up to 32 per warp);
+//   * count < kLocalMin (sparse stragglers; hybrid launches only): appends their indices to the global worklist
+//     exactly like sincos_stream_kernel, and the second-pass kernel reduces them densely packed.  A lone lane would
+//     otherwise cost the warp a whole ~250-instruction round at 1/32 utilisation and, worse, keep the block's
+//     registers and shared memory occupied while it runs (throughput here follows occupancy closely: 5 instead of
+//     6 resident blocks costs 25 %).  At most kLocalMin-1 of a warp's 128 elements are ever pushed, so the global
+//     list cannot overflow its n/32 entries in the default geometry (and the rescan covers any other geometry).
+// Measured crossover (tools/ab_quick.py): a local round costs ~300 ps, a global entry ~100 ps -> kLocalMin = 4.
+constexpr uint32_t kLocalMin = 4;
+
+template <int CORE, int OUT>
+__device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64_t xb, const uint64_t* table) {
+    uint64_t sb, cb;
+    const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);
+    if (OUT != OUT_COS) a.sin_out[e] = __longlong_as_double((long long)sb);
+    if (OUT != OUT_SIN) a.cos_out[e] = __longlong_as_double((long long)cb);
+    if (a.k_out) a.k_out[e] = q;
+}
+
+template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
+__global__ void __launch_bounds__(kThreads, FABE13_FUSED_MIN_BLOCKS) sincos_fused_kernel(const StreamArgs a) {
+    constexpr int kWarpElems = 32 * UNROLL * VEC;    // elements one warp owns per tile
+    constexpr int kTileElems = kThreads * UNROLL * VEC;
+    constexpr int kWarps = kThreads / 32;
+    static_assert(kTileElems <= 65536, "offsets inside a tile are stored as 16-bit values");
+    // per-warp worklists: no block-wide barrier anywhere, a warp only ever touches its own slice
+    __shared__ uint64_t s_x[kWarps][kWarpElems];     // arguments of the warp's Payne-Hanek lanes, compacted
+    __shared__ uint16_t s_off[kWarps][kWarpElems];   // their element offsets inside the tile
+    __shared__ uint64_t s_table[kWarps][FABE13_PH_WORDS + 3];  // a private copy of the 2/pi table per warp
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const double* in = a.in + a.head;
+    double* so = (OUT != OUT_COS) ? a.sin_out + a.head : nullptr;
+    double* co = (OUT != OUT_SIN) ? a.cos_out + a.head : nullptr;
+
+    for (uint32_t chunk = blockIdx.x; chunk * a.tiles_per_block < a.ntiles; chunk += gridDim.x) {
+        const uint32_t tile_end = min(a.ntiles, (chunk + 1) * a.tiles_per_block);
+        for (uint32_t tile = chunk * a.tiles_per_block; tile < tile_end; ++tile) {
+            const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
+            uint64_t xb[UNROLL][VEC];
+            bool live[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t v = v0 + u * kThreads;
+                live[u] = v < a.nvec;
+                if (live[u]) {
+                    load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) xb[u][j] = 0x3FF0000000000000ull;  // 1.0: a plain lane
+                }
+            }
+            bool all_plain = true;
+            uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
+            long long kk[UNROLL][VEC];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (live[u]) {
+                    const size_t e = (size_t)(v0 + u * kThreads) * VEC;
+                    if (OUT != OUT_COS) store_stream<VEC>(so + e, sb[u]);
+                    if (OUT != OUT_SIN) store_stream<VEC>(co + e, cb[u]);
+                    if (WITH_K) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
+                    }
+                }
+            }
+            // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
+            if (__ballot_sync(0xFFFFFFFFu, !all_plain) != 0) {  // rare: tiny, special or Payne-Hanek-range lanes
+                uint32_t n_huge = 0;
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
+                }
+                if (__ballot_sync(0xFFFFFFFFu, n_huge != 0) != 0) {
+                    uint32_t incl = n_huge;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if ((int)lane >= d) incl += t;
+                    }
+                    const uint32_t count = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    uint32_t slot = incl - n_huge;
+                    if (count >= kLocalMin || a.wl.counters == nullptr) {
+                        // compact this warp's Payne-Hanek lanes into its shared-memory list ...
+                        if (lane < FABE13_PH_WORDS) s_table[warp][lane] = c_ph_table[lane];
+#pragma unroll
+                        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) {
+                                if (is_stashed(xb[u][j])) {
+                                    s_x[warp][slot] = xb[u][j];
+                                    s_off[warp][slot] = (uint16_t)((u * kThreads + threadIdx.x) * VEC + j);
+                                    ++slot;
+                                }
+                            }
+                        }
+                        // ... and reduce them with all lanes busy.  __syncwarp orders the list writes before the
+                        // reads, and the placeholder vector stores above before the 8-byte result stores below.
+                        __syncwarp();
+                        const size_t tile_base = (size_t)a.head + (size_t)tile * kTileElems;
+                        for (uint32_t i = lane; i < count; i += 32)
+                            store_huge<CORE, OUT>(a, tile_base + s_off[warp][i], s_x[warp][i], s_table[warp]);
+                        __syncwarp();  // the list is reused by the warp's next tile
+                    } else {
+                        // a few stragglers: leave them, parked in their output slots, to the second-pass kernel
+                        grid_dependency_wait();  // the counters must have been zeroed (this kernel may have started early)
+                        const uint32_t seg = blockIdx.x % kSegments;
+                        uint32_t base = 0;
+                        if (lane == 31) base = atomicAdd(a.wl.counters + seg * kCounterStrideWords, count);
+                        slot += __shfl_sync(0xFFFFFFFFu, base, 31);
+                        uint32_t* seg_entries = a.wl.entries + (size_t)seg * a.wl.seg_cap;
+#pragma unroll
+                        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) {
+                                if (is_stashed(xb[u][j])) {
+                                    if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
+                                    ++slot;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // edges: the < VEC elements in front of the aligned body and the < VEC behind it (block 0, first warp)
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const uint32_t body_end = a.head + a.nvec * VEC;
+        const uint32_t n_edge = a.head + (a.n - body_end);
+        if (lane < n_edge) {
+            const uint32_t idx = lane < a.head ? lane : body_end + (lane - a.head);
+            const uint64_t xb = (uint64_t)__double_as_longlong(a.in[idx]);
+            uint64_t sb, cb;
+            int64_t k;
+            fabe13_sincos_one<CORE>(xb, c_ph_table, &sb, &cb, &k);
+            if (OUT != OUT_COS) a.sin_out[idx] = __longlong_as_double((long long)sb);
+            if (OUT != OUT_SIN) a.cos_out[idx] = __longlong_as_double((long long)cb);
+            if (WITH_K) a.k_out[idx] = k;
+        }
+    }
+}
+
 struct SecondPassArgs {
     double* sin_out;   // either may be null (single-output launches); the stash is in sin_out if present, else cos_out
     double* cos_out;
@@ -394,31 +562,45 @@ cudaError_t launch_1arg(void (*kernel)(Arg), const Arg& arg, int grid, int block
 }
 
 template <int CORE, int VEC, bool WITH_K, int OUT>
-cudaError_t launch_stream_unroll(const StreamArgs& a, int unroll, int grid, cudaStream_t stream) {
+cudaError_t launch_stream_unroll(const StreamArgs& a, bool fused, int unroll, int grid, cudaStream_t stream) {
+    if (fused) {
+        if (unroll == 2) return launch_1arg(sincos_fused_kernel<CORE, VEC, 2, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
+        return launch_1arg(sincos_fused_kernel<CORE, VEC, 1, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
+    }
     if (unroll == 2) return launch_1arg(sincos_stream_kernel<CORE, VEC, 2, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
     return launch_1arg(sincos_stream_kernel<CORE, VEC, 1, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
 }
 
 template <int CORE, bool WITH_K, int OUT>
-cudaError_t launch_stream_vec(const StreamArgs& a, int vec, int unroll, int grid, cudaStream_t stream) {
+cudaError_t launch_stream_vec(const StreamArgs& a, bool fused, int vec, int unroll, int grid, cudaStream_t stream) {
     switch (vec) {
-        case 4: return launch_stream_unroll<CORE, 4, WITH_K, OUT>(a, unroll, grid, stream);
-        case 2: return launch_stream_unroll<CORE, 2, WITH_K, OUT>(a, unroll, grid, stream);
-        default: return launch_stream_unroll<CORE, 1, WITH_K, OUT>(a, unroll, grid, stream);
+        case 4: return launch_stream_unroll<CORE, 4, WITH_K, OUT>(a, fused, unroll, grid, stream);
+        case 2: return launch_stream_unroll<CORE, 2, WITH_K, OUT>(a, fused, unroll, grid, stream);
+        default: return launch_stream_unroll<CORE, 1, WITH_K, OUT>(a, fused, unroll, grid, stream);
     }
 }
 
 template <int CORE>
-cudaError_t launch_stream(const StreamArgs& a, int vec, int unroll, int grid, cudaStream_t stream) {
+cudaError_t launch_stream(const StreamArgs& a, bool fused, int vec, int unroll, int grid, cudaStream_t stream) {
     if (a.sin_out && a.cos_out)
-        return a.k_out ? launch_stream_vec<CORE, true, OUT_BOTH>(a, vec, unroll, grid, stream)
-                       : launch_stream_vec<CORE, false, OUT_BOTH>(a, vec, unroll, grid, stream);
-    if (a.sin_out) return launch_stream_vec<CORE, false, OUT_SIN>(a, vec, unroll, grid, stream);
-    return launch_stream_vec<CORE, false, OUT_COS>(a, vec, unroll, grid, stream);
+        return a.k_out ? launch_stream_vec<CORE, true, OUT_BOTH>(a, fused, vec, unroll, grid, stream)
+                       : launch_stream_vec<CORE, false, OUT_BOTH>(a, fused, vec, unroll, grid, stream);
+    if (a.sin_out) return launch_stream_vec<CORE, false, OUT_SIN>(a, fused, vec, unroll, grid, stream);
+    return launch_stream_vec<CORE, false, OUT_COS>(a, fused, vec, unroll, grid, stream);
 }
 
-uint32_t segment_capacity(size_t n, const LaunchTuning& t) {
-    size_t cap = n >> t.worklist_shift;
+// Which Payne-Hanek worklist a launch over n elements uses (LaunchTuning::worklist; 0 = pick by size).
+enum { WL_AUTO = 0, WL_GLOBAL = 1, WL_LOCAL = 2, WL_HYBRID = 3 };
+int worklist_mode(size_t n, const LaunchTuning& t) {
+    if (t.worklist != WL_AUTO) return t.worklist;
+    // large arrays: the two extra (tiny, PDL-chained) launches of the hybrid sequence cost < 2 % and keep sparse
+    // stragglers off the streaming blocks; below that, one launch wins
+    return n >= (size_t)t.hybrid_min_n ? WL_HYBRID : WL_LOCAL;
+}
+
+uint32_t segment_capacity(size_t n, const LaunchTuning& t, int mode) {
+    // hybrid: at most kLocalMin-1 of every 128 elements are pushed -> n/32 entries are plenty
+    size_t cap = mode == WL_HYBRID ? n >> 5 : n >> t.worklist_shift;
     if (cap < 4096) cap = 4096;
     return (uint32_t)((cap + kSegments - 1) / kSegments);
 }
@@ -427,13 +609,17 @@ template <int CORE>
 cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
                         const LaunchTuning& t, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                         int* launches) {
-    if (n < (size_t)t.small_n || workspace == nullptr) {
+    int mode = worklist_mode(n, t);
+    if (mode != WL_LOCAL && workspace == nullptr) mode = WL_LOCAL;  // no scratch: everything stays in the block
+    const bool fused = mode != WL_GLOBAL;
+    if (n < (size_t)t.small_n) {
         const long long need = (long long)((n + kThreads - 1) / kThreads);
         const long long cap = (long long)dev.sm_count * 64;
         sincos_inline_kernel<CORE><<<(int)(need < cap ? need : cap), kThreads, 0, stream>>>(d_in, d_sin, d_cos, d_k, (uint32_t)n);
         *launches += 1;
         return cudaGetLastError();
     }
+    if (d_k && !(d_sin && d_cos)) return cudaErrorInvalidValue;  // the k hook exists for the sincos entry only
 
     // widest vector all arrays can share: they must be congruent modulo the vector size
     const uintptr_t pi = (uintptr_t)d_in, ps = (uintptr_t)(d_sin ? d_sin : d_cos), pc = (uintptr_t)(d_cos ? d_cos : d_sin);
@@ -459,9 +645,26 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     a.head = head;
     a.nvec = (uint32_t)((n - head) / vec);
     a.ntiles = (uint32_t)(((size_t)a.nvec + (size_t)kThreads * unroll - 1) / ((size_t)kThreads * unroll));
+    // blocks_per_sm == 0: one chunk of tiles_per_block tiles per block (the block scheduler walks the array in
+    // address order); otherwise a persistent grid of SMs*blocks_per_sm blocks strides over the chunks.
+    a.tiles_per_block = (uint32_t)(t.tiles_per_block > 0 ? t.tiles_per_block : 1);
+    long long grid = ((long long)a.ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
+    if (t.blocks_per_sm > 0 && grid > (long long)dev.sm_count * t.blocks_per_sm) grid = (long long)dev.sm_count * t.blocks_per_sm;
+    if (grid < 1) grid = 1;
+
+    if (mode == WL_LOCAL) {  // one launch, no scratch
+        a.wl.counters = nullptr;
+        a.wl.entries = nullptr;
+        a.wl.seg_cap = 0;
+        a.pdl = false;
+        *launches += 1;
+        return launch_stream<CORE>(a, true, vec, unroll, (int)grid, stream);
+    }
+
+    // global or hybrid: zero the counters -> streaming kernel -> second pass over the global worklist
     a.wl.counters = (unsigned int*)workspace;
     a.wl.entries = (uint32_t*)((char*)workspace + kWorklistHeaderBytes);
-    a.wl.seg_cap = segment_capacity(n, t);
+    a.wl.seg_cap = segment_capacity(n, t, mode);
 
     a.pdl = t.pdl != 0;
     cudaError_t err;
@@ -472,15 +675,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
         err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
     }
     if (err != cudaSuccess) return err;
-
-    // blocks_per_sm == 0: one chunk of tiles_per_block tiles per block (the block scheduler walks the array in
-    // address order); otherwise a persistent grid of SMs*blocks_per_sm blocks strides over the chunks.
-    a.tiles_per_block = (uint32_t)(t.tiles_per_block > 0 ? t.tiles_per_block : 1);
-    long long grid = ((long long)a.ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
-    if (t.blocks_per_sm > 0 && grid > (long long)dev.sm_count * t.blocks_per_sm) grid = (long long)dev.sm_count * t.blocks_per_sm;
-    if (grid < 1) grid = 1;
-    if (d_k && !(d_sin && d_cos)) return cudaErrorInvalidValue;  // the k hook exists for the sincos entry only
-    err = launch_stream<CORE>(a, vec, unroll, (int)grid, stream);
+    err = launch_stream<CORE>(a, fused, vec, unroll, (int)grid, stream);
     if (err != cudaSuccess) return err;
 
     SecondPassArgs b;
@@ -497,7 +692,9 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
 }  // namespace
 
 size_t workspace_bytes(size_t n, const LaunchTuning& t) {
-    return (size_t)kWorklistHeaderBytes + (size_t)kSegments * segment_capacity(n, t) * sizeof(uint32_t);
+    const int mode = worklist_mode(n, t);
+    if (mode == WL_LOCAL) return 0;  // the warp-local worklists live in shared memory
+    return (size_t)kWorklistHeaderBytes + (size_t)kSegments * segment_capacity(n, t, mode) * sizeof(uint32_t);
 }
 
 cudaError_t fill_uniform(double* d_out, size_t n, uint64_t seed, uint64_t first, double lo, double hi,

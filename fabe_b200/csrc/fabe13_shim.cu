@@ -40,6 +40,8 @@ const uint64_t h_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
 // ---------------------------------------------------------------------------------------------------------------
 struct Config {
     std::atomic<long long> core{FABE13_CORE_POLY};
+    std::atomic<long long> worklist{0};
+    std::atomic<long long> hybrid_min_n{(long long)1 << 26};
     std::atomic<long long> blocks_per_sm{0};
     std::atomic<long long> tiles_per_block{1};
     std::atomic<long long> pdl{1};
@@ -67,6 +69,8 @@ struct OptionDesc {
 
 const OptionDesc kOptions[] = {
     {"core", "FABE13_CUDA_CORE", &Config::core, 0, 1},
+    {"worklist", "FABE13_CUDA_WORKLIST", &Config::worklist, 0, 3},
+    {"hybrid_min_n", "FABE13_CUDA_HYBRID_MIN_N", &Config::hybrid_min_n, 0, (long long)1 << 31},
     {"blocks_per_sm", "FABE13_CUDA_BLOCKS_PER_SM", &Config::blocks_per_sm, 0, 64},
     {"tiles_per_block", "FABE13_CUDA_TILES_PER_BLOCK", &Config::tiles_per_block, 1, 1024},
     {"pdl", "FABE13_CUDA_PDL", &Config::pdl, 0, 1},
@@ -98,6 +102,8 @@ void load_env() {
 LaunchTuning current_tuning() {
     load_env();
     LaunchTuning t;
+    t.worklist = (int)g_cfg.worklist.load();
+    t.hybrid_min_n = (int)(g_cfg.hybrid_min_n.load() > 0x7FFFFFFFll ? 0x7FFFFFFFll : g_cfg.hybrid_min_n.load());
     t.blocks_per_sm = (int)g_cfg.blocks_per_sm.load();
     t.tiles_per_block = (int)g_cfg.tiles_per_block.load();
     t.pdl = (int)g_cfg.pdl.load();
@@ -204,8 +210,8 @@ int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k,
         const size_t m = (n - off < kLaunchMaxElems) ? n - off : kLaunchMaxElems;
         void* ws = nullptr;
         bool pooled = false;
-        if (m >= (size_t)t.small_n) {
-            const size_t need = fabe13::workspace_bytes(m, t);
+        const size_t need = m >= (size_t)t.small_n ? fabe13::workspace_bytes(m, t) : 0;
+        if (need > 0) {
             if (user_ws) {
                 if (user_ws_bytes < need) return record(cudaErrorInvalidValue, "workspace too small");
                 ws = user_ws;
@@ -276,7 +282,7 @@ int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning&
     }
     // the worklist scratch depends on the tuning in force (option worklist_shift may change between calls)
     const size_t need_ws = fabe13::workspace_bytes(s.chunk_cap, t);
-    if (s.ws_bytes < need_ws) {
+    if (need_ws > 0 && s.ws_bytes < need_ws) {
         for (Slot& sl : s.slots) {
             if (sl.d_ws) FABE13_TRY(cudaFree(sl.d_ws));
             sl.d_ws = nullptr;
@@ -318,7 +324,7 @@ int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, 
     FABE13_TRY(cudaMemcpyAsync(sl.d_in, src, m * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
     int launches = 0;
     cudaError_t e = fabe13::launch_sincos(sl.d_in, dst_sin ? sl.d_sin : nullptr, dst_cos ? sl.d_cos : nullptr, nullptr, m, core,
-                                          t, s.info, m >= (size_t)t.small_n ? sl.d_ws : nullptr, sl.stream, &launches);
+                                          t, s.info, (m >= (size_t)t.small_n && fabe13::workspace_bytes(m, t) > 0) ? sl.d_ws : nullptr, sl.stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
     if (e != cudaSuccess) return record(e, "launch_sincos(host path)");
     if (dst_sin) FABE13_TRY(cudaMemcpyAsync(dst_sin, sl.d_sin, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
@@ -358,8 +364,9 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
     }
     int launches = 0;
     void* ws = nullptr;
-    if (n >= (size_t)t.small_n)  // large enough for the streaming kernel: it needs its worklist scratch
-        FABE13_TRY(cudaMallocFromPoolAsync(&ws, fabe13::workspace_bytes(n, t), s.pool, s.small_stream));
+    const size_t need_ws = n >= (size_t)t.small_n ? fabe13::workspace_bytes(n, t) : 0;
+    if (need_ws > 0)  // a global worklist is in play: the launch sequence needs its scratch
+        FABE13_TRY(cudaMallocFromPoolAsync(&ws, need_ws, s.pool, s.small_stream));
     cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, core, t, s.info, ws,
                                           s.small_stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
@@ -623,7 +630,8 @@ size_t fabe13_sincos_workspace_bytes(size_t n) {
 
 int fabe13_sincos_device_ws(const double* d_in, double* d_sin, double* d_cos, size_t n, void* workspace,
                             size_t workspace_bytes, void* cuda_stream) {
-    if (!workspace) return record(cudaErrorInvalidValue, "fabe13_sincos_device_ws: null workspace");
+    if (!workspace && fabe13_sincos_workspace_bytes(n) > 0)
+        return record(cudaErrorInvalidValue, "fabe13_sincos_device_ws: null workspace");
     return run_device(d_in, d_sin, d_cos, nullptr, n, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
 }
 

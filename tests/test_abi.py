@@ -95,8 +95,17 @@ def test_options_roundtrip_and_validation(fabe13):
     with pytest.raises(KeyError):
         fabe13.get_option("no_such_option")
     assert fabe13.get_option("launches") >= 0
-    ws = fabe13._lib.load().fabe13_sincos_workspace_bytes(10**8) if hasattr(fabe13, "_lib") else None
-    assert ws is None or ws >= 32 + 4 * (10**8 >> 3)
+    lib = fabe13._lib.load()
+    assert fabe13.get_option("worklist") == 0          # default: by size
+    assert lib.fabe13_sincos_workspace_bytes(10**7) == 0                      # warp-local lists in shared memory
+    assert lib.fabe13_sincos_workspace_bytes(10**8) >= 4096 + 4 * (10**8 >> 5)  # hybrid: header + n/32 entries
+    try:
+        fabe13.set_option("worklist", 1)               # global worklist alone: header + n/8 32-bit entries
+        assert lib.fabe13_sincos_workspace_bytes(10**7) >= 4096 + 4 * (10**7 >> 3)
+        fabe13.set_option("worklist", 2)               # local only: never any scratch
+        assert lib.fabe13_sincos_workspace_bytes(10**9) == 0
+    finally:
+        fabe13.set_option("worklist", 0)
 
 
 def test_n_le_zero_is_a_silent_noop(fabe13):

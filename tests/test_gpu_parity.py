@@ -38,9 +38,29 @@ def gpu_sincos(fabe13, cuda, x):
     return s.cpu().numpy(), c.cpu().numpy()
 
 
-@pytest.fixture(autouse=True)
-def _defaults(fabe13):
-    saved = {k: fabe13.get_option(k) for k in ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift", "pdl")}
+# Every test runs three times, once per Payne-Hanek worklist design: the default (option worklist=0: warp-local lists
+# in shared memory and a single launch below hybrid_min_n elements, the hybrid sequence from there on), the global
+# worklist + second-pass kernel alone (worklist=1), and the hybrid sequence forced at every size (worklist=3).  The
+# heaviest cases run in the default mode only; the tests of the global worklist's own machinery (capacity/overflow
+# rescan, PDL, caller workspace) are skipped where no global worklist exists.
+HEAVY = {"test_c3_1e9_properties", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
+         "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
+         "test_mixed_host_device_pointers_fail_loudly", "test_native_library_is_the_one_running"}
+GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
+               "test_host_path_survives_tuning_changes_between_calls"}
+OPTIONS = ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift",
+           "pdl", "worklist", "hybrid_min_n")
+
+
+@pytest.fixture(autouse=True, params=[0, 1, 3], ids=["auto-worklist", "global-worklist", "hybrid-worklist"])
+def _defaults(request, fabe13):
+    name = request.node.originalname
+    if request.param != 0 and name in HEAVY:
+        pytest.skip("heavy case: default mode only")
+    if request.param == 0 and name in GLOBAL_ONLY:
+        pytest.skip("exercises the global worklist's machinery")
+    saved = {k: fabe13.get_option(k) for k in OPTIONS}
+    fabe13.set_option("worklist", request.param)
     yield
     for k, v in saved.items():
         fabe13.set_option(k, v)
@@ -256,6 +276,9 @@ def test_caller_provided_workspace(fabe13, cuda, oracle):
     assert rc == 0
     torch.cuda.synchronize()
     check_against_oracle(x, s.cpu().numpy(), c.cpu().numpy(), None, oracle, label="caller workspace")
+    if need == 0:  # warp-local worklists only: no scratch at all, a null workspace is legal
+        assert fabe13.get_option("worklist") == 0
+        return
     # too small a workspace is refused loudly, not silently accepted
     rc = lib.fabe13_sincos_device_ws(xt.data_ptr(), s.data_ptr(), c.data_ptr(), n, ws.data_ptr(), 64, None)
     assert rc != 0 and lib.fabe13_cuda_last_error() != 0
