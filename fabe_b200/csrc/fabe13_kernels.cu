@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
 //     list cannot overflow its n/32 entries in the default geometry (and the rescan covers any other geometry).
 // Measured crossover (tools/ab_quick.py): a local round costs ~300 ps, a global entry ~100 ps -> kLocalMin = 4.
 constexpr uint32_t kLocalMin = 4;
+// lanes (of 32) whose first element must be non-plain for the warp to take the dense route
+constexpr uint32_t kDenseHint = 24;
 
 template <int CORE, int OUT>
 __device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64_t xb, const uint64_t* table) {
@@ -280,118 +282,194 @@ __device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64
     if (a.k_out) a.k_out[e] = q;
 }
 
-template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
-__global__ void __launch_bounds__(kThreads, FABE13_FUSED_MIN_BLOCKS) sincos_fused_kernel(const StreamArgs a) {
-    constexpr int kWarpElems = 32 * UNROLL * VEC;    // elements one warp owns per tile
-    constexpr int kTileElems = kThreads * UNROLL * VEC;
-    constexpr int kWarps = kThreads / 32;
-    static_assert(kTileElems <= 65536, "offsets inside a tile are stored as 16-bit values");
+template <int UNROLL, int VEC>
+struct FusedShared {
+    static constexpr int kWarpElems = 32 * UNROLL * VEC;  // elements one warp owns per tile
+    static constexpr int kWarps = kThreads / 32;
     // per-warp worklists: no block-wide barrier anywhere, a warp only ever touches its own slice
-    __shared__ uint64_t s_x[kWarps][kWarpElems];     // arguments of the warp's Payne-Hanek lanes, compacted
-    __shared__ uint16_t s_off[kWarps][kWarpElems];   // their element offsets inside the tile
-    __shared__ uint64_t s_table[kWarps][FABE13_PH_WORDS + 3];  // a private copy of the 2/pi table per warp
+    uint64_t x[kWarps][kWarpElems];               // arguments of the warp's Payne-Hanek lanes, compacted
+    uint64_t c[kWarps][kWarpElems];               // dense route: cosine results on their way back to their lanes
+    uint64_t table[kWarps][FABE13_PH_WORDS + 3];  // a private copy of the 2/pi table per warp
+    uint16_t off[kWarps][kWarpElems];             // their element offsets inside the tile
+};
+
+// The rounds of the dense-warp route (see fused_tile).  Not inlined: its register allocation must not leak into the
+// streaming path (inlined, ptxas spilled the fast path's live vectors around it).  The caller has parked the lane's
+// arguments in sh.x[warp][r*32 + lane], r = u*VEC + j, and picks the results up from sh.x (sines) and sh.c (cosines)
+// at the same positions.  (The 256-bit stores stay with the caller: inside this function ptxas 12.9 turned
+// st.global.cs.v4.b64 into a 64-bit store of the first element in one of the two kernels it was cloned into.)
+template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
+__device__ __noinline__ void dense_rounds(long long* k_out, uint32_t head, uint32_t nvec, uint32_t v0,
+                                          FusedShared<UNROLL, VEC>& sh) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    if (lane < FABE13_PH_WORDS) sh.table[warp][lane] = c_ph_table[lane];
+    __syncwarp();  // the table is complete
+#pragma unroll 1
+    for (uint32_t r = 0; r < (uint32_t)(UNROLL * VEC); ++r) {
+        uint64_t s1, c1;
+        int64_t k;
+        fabe13_sincos_one<CORE>(sh.x[warp][r * 32 + lane], sh.table[warp], &s1, &c1, &k);
+        sh.x[warp][r * 32 + lane] = s1;
+        sh.c[warp][r * 32 + lane] = c1;
+        if (WITH_K) {
+            const uint32_t v = v0 + (r / VEC) * kThreads;
+            if (v < nvec) k_out[head + (size_t)v * VEC + r % VEC] = k;
+        }
+    }
+}
+
+// one tile of kThreads*UNROLL vectors: stream it, then deal with its Payne-Hanek lanes
+template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
+__device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, FusedShared<UNROLL, VEC>& sh) {
+    constexpr int kTileElems = kThreads * UNROLL * VEC;
+    static_assert(kTileElems <= 65536, "offsets inside a tile are stored as 16-bit values");
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     const double* in = a.in + a.head;
     double* so = (OUT != OUT_COS) ? a.sin_out + a.head : nullptr;
     double* co = (OUT != OUT_SIN) ? a.cos_out + a.head : nullptr;
-
-    for (uint32_t chunk = blockIdx.x; chunk * a.tiles_per_block < a.ntiles; chunk += gridDim.x) {
-        const uint32_t tile_end = min(a.ntiles, (chunk + 1) * a.tiles_per_block);
-        for (uint32_t tile = chunk * a.tiles_per_block; tile < tile_end; ++tile) {
-            const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
-            uint64_t xb[UNROLL][VEC];
-            bool live[UNROLL];
+    auto& s_x = sh.x;
+    auto& s_off = sh.off;
+    auto& s_table = sh.table;
+    const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
+    uint64_t xb[UNROLL][VEC];
+    bool live[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t v = v0 + u * kThreads;
-                live[u] = v < a.nvec;
-                if (live[u]) {
-                    load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
-                } else {
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t v = v0 + u * kThreads;
+        live[u] = v < a.nvec;
+        if (live[u]) {
+            load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
+        } else {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) xb[u][j] = 0x3FF0000000000000ull;  // 1.0: a plain lane
-                }
+            for (int j = 0; j < VEC; ++j) xb[u][j] = 0x3FF0000000000000ull;  // 1.0: a plain lane
+        }
+    }
+    bool all_plain = true, dense = false;
+    uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
+    long long kk[UNROLL][VEC];
+    // Dense-warp route.  One early vote on each lane's first element (its plain/non-plain predicate is needed by
+    // the fast path anyway): if most of them are not plain, the tile is presumably full of Payne-Hanek arguments,
+    // and running the fast path first only to redo nearly every lane would waste a quarter of the work.  Such a
+    // warp hands all its elements to the every-range routine instead, one element slot of every lane per round.
+    // Arguments and results pass through the lane's own entries of the warp's shared-memory slice, only so that
+    // the rounds can be a rolled loop (registers cannot be indexed by a loop counter) and the results still leave
+    // as the same two 256-bit stores per vector as on the fast path (scattered 8-byte stores of a dense tile are
+    // bound by L2 sector transactions: measured 98 instead of 120 Gelem/s).  Lanes split for the reduction only
+    // (Payne-Hanek vs Cody-Waite) and share core and fix-up; a round in which no lane holds a Payne-Hanek argument
+    // skips that branch altogether, so interleaved data (every 4th element huge, say) costs one such reduction
+    // per tile, not four.  A wrong guess costs nothing but time: the routine is complete for every input.
+    if (__popc(__ballot_sync(0xFFFFFFFFu, !fabe13_is_plain(fabe13_abs_hi(xb[0][0])))) >= (int)kDenseHint) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) s_x[warp][(u * VEC + j) * 32 + lane] = xb[u][j];
+        }
+        dense_rounds<CORE, VEC, UNROLL, WITH_K, OUT>(a.k_out, a.head, a.nvec, v0, sh);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                sb[u][j] = s_x[warp][(u * VEC + j) * 32 + lane];
+                cb[u][j] = sh.c[warp][(u * VEC + j) * 32 + lane];
             }
-            bool all_plain = true;
-            uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
-            long long kk[UNROLL][VEC];
+        }
+        __syncwarp();  // the slice is reused by the warp's next tile
+        dense = true;
+    } else {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+            for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        if (live[u]) {
+            const size_t e = (size_t)(v0 + u * kThreads) * VEC;
+            if (OUT != OUT_COS) store_stream<VEC>(so + e, sb[u]);
+            if (OUT != OUT_SIN) store_stream<VEC>(co + e, cb[u]);
+            if (WITH_K && !dense) {  // (the dense route has written its k values itself)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
             }
+        }
+    }
+    // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
+    if (__ballot_sync(0xFFFFFFFFu, !all_plain) != 0) {  // rare: tiny, special or Payne-Hanek-range lanes
+        uint32_t n_huge = 0;
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                if (live[u]) {
-                    const size_t e = (size_t)(v0 + u * kThreads) * VEC;
-                    if (OUT != OUT_COS) store_stream<VEC>(so + e, sb[u]);
-                    if (OUT != OUT_SIN) store_stream<VEC>(co + e, cb[u]);
-                    if (WITH_K) {
+        for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
-                    }
-                }
+            for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
+        }
+        if (__ballot_sync(0xFFFFFFFFu, n_huge != 0) != 0) {
+            uint32_t incl = n_huge;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if ((int)lane >= d) incl += t;
             }
-            // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
-            if (__ballot_sync(0xFFFFFFFFu, !all_plain) != 0) {  // rare: tiny, special or Payne-Hanek-range lanes
-                uint32_t n_huge = 0;
+            const uint32_t count = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            uint32_t slot = incl - n_huge;
+            if (count >= kLocalMin || a.wl.counters == nullptr) {
+                // compact this warp's Payne-Hanek lanes into its shared-memory list ...
+                if (lane < FABE13_PH_WORDS) s_table[warp][lane] = c_ph_table[lane];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
-                }
-                if (__ballot_sync(0xFFFFFFFFu, n_huge != 0) != 0) {
-                    uint32_t incl = n_huge;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                        if ((int)lane >= d) incl += t;
-                    }
-                    const uint32_t count = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                    uint32_t slot = incl - n_huge;
-                    if (count >= kLocalMin || a.wl.counters == nullptr) {
-                        // compact this warp's Payne-Hanek lanes into its shared-memory list ...
-                        if (lane < FABE13_PH_WORDS) s_table[warp][lane] = c_ph_table[lane];
-#pragma unroll
-                        for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) {
-                                if (is_stashed(xb[u][j])) {
-                                    s_x[warp][slot] = xb[u][j];
-                                    s_off[warp][slot] = (uint16_t)((u * kThreads + threadIdx.x) * VEC + j);
-                                    ++slot;
-                                }
-                            }
+                    for (int j = 0; j < VEC; ++j) {
+                        if (is_stashed(xb[u][j])) {
+                            s_x[warp][slot] = xb[u][j];
+                            s_off[warp][slot] = (uint16_t)((u * kThreads + threadIdx.x) * VEC + j);
+                            ++slot;
                         }
-                        // ... and reduce them with all lanes busy.  __syncwarp orders the list writes before the
-                        // reads, and the placeholder vector stores above before the 8-byte result stores below.
-                        __syncwarp();
-                        const size_t tile_base = (size_t)a.head + (size_t)tile * kTileElems;
-                        for (uint32_t i = lane; i < count; i += 32)
-                            store_huge<CORE, OUT>(a, tile_base + s_off[warp][i], s_x[warp][i], s_table[warp]);
-                        __syncwarp();  // the list is reused by the warp's next tile
-                    } else {
-                        // a few stragglers: leave them, parked in their output slots, to the second-pass kernel
-                        grid_dependency_wait();  // the counters must have been zeroed (this kernel may have started early)
-                        const uint32_t seg = blockIdx.x % kSegments;
-                        uint32_t base = 0;
-                        if (lane == 31) base = atomicAdd(a.wl.counters + seg * kCounterStrideWords, count);
-                        slot += __shfl_sync(0xFFFFFFFFu, base, 31);
-                        uint32_t* seg_entries = a.wl.entries + (size_t)seg * a.wl.seg_cap;
+                    }
+                }
+                // ... and reduce them with all lanes busy.  __syncwarp orders the list writes before the
+                // reads, and the placeholder vector stores above before the 8-byte result stores below.
+                __syncwarp();
+                const size_t tile_base = (size_t)a.head + (size_t)tile * kTileElems;
+                for (uint32_t i = lane; i < count; i += 32)
+                    store_huge<CORE, OUT>(a, tile_base + s_off[warp][i], s_x[warp][i], s_table[warp]);
+                __syncwarp();  // the list is reused by the warp's next tile
+            } else {
+                // a few stragglers: leave them, parked in their output slots, to the second-pass kernel
+                grid_dependency_wait();  // the counters must have been zeroed (this kernel may have started early)
+                const uint32_t seg = blockIdx.x % kSegments;
+                uint32_t base = 0;
+                if (lane == 31) base = atomicAdd(a.wl.counters + seg * kCounterStrideWords, count);
+                slot += __shfl_sync(0xFFFFFFFFu, base, 31);
+                uint32_t* seg_entries = a.wl.entries + (size_t)seg * a.wl.seg_cap;
 #pragma unroll
-                        for (int u = 0; u < UNROLL; ++u) {
+                for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) {
-                                if (is_stashed(xb[u][j])) {
-                                    if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
-                                    ++slot;
-                                }
-                            }
+                    for (int j = 0; j < VEC; ++j) {
+                        if (is_stashed(xb[u][j])) {
+                            if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
+                            ++slot;
                         }
                     }
                 }
             }
+        }
+    }
+}
+
+// ONE_TILE: block b owns tile b (the default geometry: no loop state to keep in registers); otherwise blocks stride
+// over chunks of tiles_per_block consecutive tiles.
+template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT, bool ONE_TILE>
+__global__ void __launch_bounds__(kThreads, FABE13_FUSED_MIN_BLOCKS) sincos_fused_kernel(const StreamArgs a) {
+    __shared__ FusedShared<UNROLL, VEC> sh;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (ONE_TILE) {
+        fused_tile<CORE, VEC, UNROLL, WITH_K, OUT>(a, blockIdx.x, sh);
+    } else {
+        for (uint32_t chunk = blockIdx.x; chunk * a.tiles_per_block < a.ntiles; chunk += gridDim.x) {
+            const uint32_t tile_end = min(a.ntiles, (chunk + 1) * a.tiles_per_block);
+            for (uint32_t tile = chunk * a.tiles_per_block; tile < tile_end; ++tile)
+                fused_tile<CORE, VEC, UNROLL, WITH_K, OUT>(a, tile, sh);
         }
     }
 
@@ -564,8 +642,10 @@ cudaError_t launch_1arg(void (*kernel)(Arg), const Arg& arg, int grid, int block
 template <int CORE, int VEC, bool WITH_K, int OUT>
 cudaError_t launch_stream_unroll(const StreamArgs& a, bool fused, int unroll, int grid, cudaStream_t stream) {
     if (fused) {
-        if (unroll == 2) return launch_1arg(sincos_fused_kernel<CORE, VEC, 2, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
-        return launch_1arg(sincos_fused_kernel<CORE, VEC, 1, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
+        const bool one_tile = (uint32_t)grid == a.ntiles && a.tiles_per_block == 1;
+        if (unroll == 2) return launch_1arg(sincos_fused_kernel<CORE, VEC, 2, WITH_K, OUT, false>, a, grid, kThreads, stream, a.pdl);
+        if (one_tile) return launch_1arg(sincos_fused_kernel<CORE, VEC, 1, WITH_K, OUT, true>, a, grid, kThreads, stream, a.pdl);
+        return launch_1arg(sincos_fused_kernel<CORE, VEC, 1, WITH_K, OUT, false>, a, grid, kThreads, stream, a.pdl);
     }
     if (unroll == 2) return launch_1arg(sincos_stream_kernel<CORE, VEC, 2, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
     return launch_1arg(sincos_stream_kernel<CORE, VEC, 1, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B of the two Payne-Hanek worklist designs on one GPU: worklist=0 (block-local list in shared memory, one fused
-launch) vs worklist=1 (global list + second-pass kernel).  C3 burst and sustained, C2, C4 dense, sparse mixes, and
+"""A/B of the Payne-Hanek worklist designs on one GPU, alternating in one process (option worklist: 0 = by size,
+1 = global list + second-pass kernel [the round-1 streaming kernel], 2 = warp-local lists, 3 = hybrid):
+    python tools/ab_worklist.py <tag> [modes, default 0,1]  C3 burst and sustained, C2, C4 dense, sparse mixes, and
 per-call GPU time for small/medium n."""
 import os
 import sys
@@ -21,13 +22,14 @@ def main():
     s = torch.empty_like(x)
     c = torch.empty_like(x)
     m = 100_000_000
-    modes = (0, 1, 0, 1)
+    pair = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 1)
+    modes = pair + pair
     fb.fill_uniform_device(x, 0xFABE1303, -1e4, 1e4)
     for wl in modes:
         fb.set_option("worklist", wl)
         avg, best = time_steps(x, s, c, steps=20)
         report(f"{tag} worklist={wl} c3 1e9 burst(20)", n, avg, best)
-    for wl in (0, 1):
+    for wl in pair:
         fb.set_option("worklist", wl)
         avg, best = time_steps(x, s, c, steps=300)
         report(f"{tag} worklist={wl} c3 1e9 sustained(300)", n, avg, best)
@@ -37,7 +39,7 @@ def main():
         report(f"{tag} worklist={wl} c2 1e8", m, avg, best)
     # small / medium calls: GPU time per call (back to back on one stream)
     for k in (10_000, 100_000, 1_000_000, 4_000_000, 10_000_000):
-        for wl in (0, 1):
+        for wl in pair:
             for small_n in (0, 1 << 22):
                 fb.set_option("worklist", wl)
                 fb.set_option("small_n", small_n)
@@ -55,14 +57,14 @@ def main():
         h = torch.empty((m + step - 1) // step, dtype=torch.float64, device=dev)
         fb.fill_loguniform_device(h, 0xFABE1304)
         x[:m][::step] = h
-        for wl in (0, 1):
+        for wl in pair:
             fb.set_option("worklist", wl)
             avg, best = time_steps(x[:m], s[:m], c[:m], steps=10)
             report(f"{tag} worklist={wl} mix {100.0 / step:.2f}% extreme n=1e8", m, avg, best)
     # zeros in the data (tiny lanes: not plain, but no Payne-Hanek work): the block vote fires on every tile
     fb.fill_uniform_device(x[:m], 0xFABE1302, -1e4, 1e4)
     x[:m][::7] = 0.0
-    for wl in (0, 1):
+    for wl in pair:
         fb.set_option("worklist", wl)
         avg, best = time_steps(x[:m], s[:m], c[:m], steps=10)
         report(f"{tag} worklist={wl} 1 zero in 7 n=1e8", m, avg, best)
