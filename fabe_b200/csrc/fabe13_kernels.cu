@@ -38,7 +38,8 @@ namespace {
 #define FABE13_BLOCK_THREADS 256
 #endif
 constexpr int kThreads = FABE13_BLOCK_THREADS;
-// resident blocks per SM the fused kernel is compiled for (register cap 65536 / (256 * 6) -> 40)
+// resident blocks per SM the fused kernel is compiled for (register cap 65536 / (256 * 6) -> 40); the Psi core is
+// FP64-pipe bound, needs ~60 registers and is compiled for 4
 #ifndef FABE13_FUSED_MIN_BLOCKS
 #define FABE13_FUSED_MIN_BLOCKS 6
 #endif
@@ -460,7 +461,8 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
 // ONE_TILE: block b owns tile b (the default geometry: no loop state to keep in registers); otherwise blocks stride
 // over chunks of tiles_per_block consecutive tiles.
 template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT, bool ONE_TILE>
-__global__ void __launch_bounds__(kThreads, FABE13_FUSED_MIN_BLOCKS) sincos_fused_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(kThreads, CORE == FABE13_CORE_PSI ? 4 : FABE13_FUSED_MIN_BLOCKS)
+    sincos_fused_kernel(const StreamArgs a) {
     __shared__ FusedShared<UNROLL, VEC> sh;
     const uint32_t lane = threadIdx.x & 31u;
     if (ONE_TILE) {

@@ -22,7 +22,9 @@ extern "C" {
 
 /* Asynchronous sincos over n device-resident doubles on `cuda_stream` (NULL = legacy default stream).
  * d_in, d_sin, d_cos are device pointers on the current device, 8-byte aligned; d_in == d_sin is allowed.
- * Scratch for the Payne-Hanek worklist is taken from a library-owned stream-ordered memory pool. */
+ * Below 2^26 elements (option "hybrid_min_n") the call is ONE kernel launch and needs no scratch memory: the
+ * Payne-Hanek worklists live in shared memory.  From there on, a global worklist for sparse huge arguments
+ * (n/32 32-bit entries) is taken from a library-owned stream-ordered memory pool. */
 int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream);
 
 /* Same, and also writes the quadrant index per element (test hook for the k-parity contract):
@@ -40,7 +42,8 @@ int fabe13_sin_host(const double* in, double* out, size_t n);
 int fabe13_cos_host(const double* in, double* out, size_t n);
 
 /* Same as fabe13_sincos_device with caller-provided scratch of at least fabe13_sincos_workspace_bytes(n) bytes
- * (no allocation on the call path; usable inside CUDA graph capture on any toolkit). */
+ * (no allocation on the call path; usable inside CUDA graph capture on any toolkit).  The size may be 0 (small n,
+ * or option "worklist" = 2); a NULL workspace is accepted exactly then. */
 size_t fabe13_sincos_workspace_bytes(size_t n);
 int fabe13_sincos_device_ws(const double* d_in, double* d_sin, double* d_cos, size_t n, void* workspace,
                             size_t workspace_bytes, void* cuda_stream);
@@ -68,7 +71,13 @@ void fabe13_cuda_host_free(void* p);
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
 
 /* Options: "core" (0/1), "unroll" (1/2), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
- * per SM), "second_pass_blocks_per_sm", "small_n", "worklist_shift", "chunk_elems", "host_devices", "stage_threads", "zero_copy_max", "tiles_per_block", "pdl" (programmatic dependent launch of the per-call kernels).  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
+ * per SM), "tiles_per_block", "small_n" (below: the one-element-per-thread kernel),
+ * "worklist" (where arguments >= 2^45 are reduced: 0 = by size [default]: in the streaming kernel's shared memory,
+ * one launch, below "hybrid_min_n" elements, plus a global list for sparse stragglers from there on; 1 = global list
+ * and second-pass kernel only [the round-1 design]; 2 = shared memory only at every size; 3 = hybrid at every size),
+ * "hybrid_min_n", "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
+ * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
+ * "zero_copy_max".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);
 int fabe13_cuda_get_option(const char* key, long long* value);

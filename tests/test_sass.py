@@ -1,0 +1,77 @@
+"""Static checks on the machine code of libfabe13.so (cuobjdump -sass; no GPU needed).
+
+The streaming kernels must move their data with 256-bit accesses (LDG.E...256 / STG.E...256: SURVEY section 8 a-3), must
+not spill on the hot path, and every kernel that produces vectors must store them as vectors.  The last check exists
+because ptxas 12.9 once turned a st.global.cs.v4.b64 inside a non-inlined device function into a 64-bit store of the
+first element (see the note on dense_rounds in csrc/fabe13_kernels.cu): results were wrong only on the GPU, and only on
+one route."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def sass(fabe13):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        out = subprocess.run([exe, "-sass", fabe13.build.LIBPATH], capture_output=True, text=True, check=True).stdout
+    except (OSError, subprocess.CalledProcessError) as e:
+        pytest.skip(f"cuobjdump unavailable: {e}")
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            funcs[name].append(line)
+    return funcs
+
+
+def pick(funcs, pattern):
+    hits = {n: body for n, body in funcs.items() if re.search(pattern, n)}
+    assert hits, f"no kernel matches {pattern}"
+    return hits
+
+
+def count(body, mnemonic):
+    return sum(1 for line in body if re.search(mnemonic, line))
+
+
+def test_library_is_built_for_sm_100a(fabe13):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        out = subprocess.run([exe, "-lelf", fabe13.build.LIBPATH], capture_output=True, text=True, check=True).stdout
+    except (OSError, subprocess.CalledProcessError) as e:
+        pytest.skip(f"cuobjdump unavailable: {e}")
+    assert "sm_100a" in out, out
+
+
+# template arguments in the mangled names: <CORE, VEC, UNROLL, WITH_K, OUT[, ONE_TILE]>
+@pytest.mark.parametrize("core", [0, 1])
+def test_default_hot_kernel_uses_256_bit_accesses_and_does_not_spill(sass, core):
+    (name, body), = pick(sass, rf"sincos_fused_kernelILi{core}ELi4ELi1ELb0ELi0ELb1E").items()
+    assert count(body, r"LDG\.E\.NA\S*\.256") == 1, name          # one vector load per thread and tile
+    assert count(body, r"STG\.E\.EF\S*\.256") == 2, name          # sines, cosines
+    assert count(body, r"\b(STL|LDL)\b") == 0, f"{name} spills registers"
+    assert count(body, r"\bBAR\b") == 0, f"{name}: the hot path must not contain a block-wide barrier"
+    assert count(body, r"\bDFMA\b") >= 18                         # the FP64 work is there (not optimised away)
+
+
+def test_every_vec4_streaming_kernel_stores_vectors(sass):
+    for name, body in pick(sass, r"sincos_(fused|stream)_kernelILi[01]ELi4E").items():
+        m = re.search(r"kernelILi[01]ELi4ELi([12])ELb[01]ELi([012])E", name)
+        unroll, out = int(m.group(1)), int(m.group(2))
+        per_vector = 2 if out == 0 else 1
+        assert count(body, r"STG\.E\.EF\S*\.256") == per_vector * unroll, name
+        assert count(body, r"LDG\.E\.NA\S*\.256") == unroll, name
+        assert count(body, r"STG\.E\.EF\.64\b") == 0, f"{name}: a vector store was narrowed"
+
+
+def test_narrower_vector_widths_exist_for_incongruent_pointers(sass):
+    assert pick(sass, r"sincos_fused_kernelILi0ELi2E")
+    assert pick(sass, r"sincos_fused_kernelILi0ELi1E")
+    for name, body in pick(sass, r"sincos_fused_kernelILi0ELi2ELi1ELb0ELi0E").items():
+        assert count(body, r"LDG\.E\.NA\S*\.128") == 1 and count(body, r"STG\.E\.EF\S*\.128") == 2, name
