@@ -49,7 +49,8 @@ constexpr int kSegments = 32;
 constexpr int kCounterStrideWords = 32;
 constexpr int kWorklistHeaderBytes = kSegments * kCounterStrideWords * 4;
 
-__constant__ uint64_t c_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
+// 2/pi as a stream of 32-bit words, most significant first (fabe13_payne_hanek reads seven consecutive words)
+__constant__ uint32_t c_ph_stream[FABE13_PH_STREAM_WORDS] = FABE13_PH_STREAM;
 
 // Programmatic dependent launch: the three launches of one call (zero the counters, stream, second pass) are queued
 // with the programmatic-serialisation attribute, so each one is staged while its predecessor still runs and the
@@ -274,8 +275,15 @@ constexpr uint32_t kLocalMin = 4;
 // lanes (of 32) whose first element must be non-plain for the warp to take the dense route
 constexpr uint32_t kDenseHint = 24;
 
+// one warp copies the 2/pi word stream into its slice of shared memory (lanes index it by their own exponent; a
+// divergent __constant__ read would serialise)
+__device__ __forceinline__ void stage_stream_warp(uint32_t* dst, uint32_t lane) {
+    dst[lane] = c_ph_stream[lane];
+    if (lane + 32 < FABE13_PH_STREAM_WORDS) dst[lane + 32] = c_ph_stream[lane + 32];
+}
+
 template <int CORE, int OUT>
-__device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64_t xb, const uint64_t* table) {
+__device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64_t xb, const uint32_t* table) {
     uint64_t sb, cb;
     const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);
     if (OUT != OUT_COS) a.sin_out[e] = __longlong_as_double((long long)sb);
@@ -290,7 +298,7 @@ struct FusedShared {
     // per-warp worklists: no block-wide barrier anywhere, a warp only ever touches its own slice
     uint64_t x[kWarps][kWarpElems];               // arguments of the warp's Payne-Hanek lanes, compacted
     uint64_t c[kWarps][kWarpElems];               // dense route: cosine results on their way back to their lanes
-    uint64_t table[kWarps][FABE13_PH_WORDS + 3];  // a private copy of the 2/pi table per warp
+    uint32_t table[kWarps][FABE13_PH_STREAM_WORDS + 6];  // a private copy of the 2/pi word stream per warp
     uint16_t off[kWarps][kWarpElems];             // their element offsets inside the tile
 };
 
@@ -304,7 +312,7 @@ __device__ __noinline__ void dense_rounds(long long* k_out, uint32_t head, uint3
                                           FusedShared<UNROLL, VEC>& sh) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    if (lane < FABE13_PH_WORDS) sh.table[warp][lane] = c_ph_table[lane];
+    stage_stream_warp(sh.table[warp], lane);
     __syncwarp();  // the table is complete
 #pragma unroll 1
     for (uint32_t r = 0; r < (uint32_t)(UNROLL * VEC); ++r) {
@@ -416,7 +424,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
             uint32_t slot = incl - n_huge;
             if (count >= kLocalMin || a.wl.counters == nullptr) {
                 // compact this warp's Payne-Hanek lanes into its shared-memory list ...
-                if (lane < FABE13_PH_WORDS) s_table[warp][lane] = c_ph_table[lane];
+                stage_stream_warp(s_table[warp], lane);
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
@@ -484,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, CORE == FABE13_CORE_PSI ? 4 : FABE13
             const uint64_t xb = (uint64_t)__double_as_longlong(a.in[idx]);
             uint64_t sb, cb;
             int64_t k;
-            fabe13_sincos_one<CORE>(xb, c_ph_table, &sb, &cb, &k);
+            fabe13_sincos_one<CORE>(xb, c_ph_stream, &sb, &cb, &k);
             if (OUT != OUT_COS) a.sin_out[idx] = __longlong_as_double((long long)sb);
             if (OUT != OUT_SIN) a.cos_out[idx] = __longlong_as_double((long long)cb);
             if (WITH_K) a.k_out[idx] = k;
@@ -501,7 +509,7 @@ struct SecondPassArgs {
 };
 
 template <int CORE>
-__device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t idx, uint64_t xb, const uint64_t* table) {
+__device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t idx, uint64_t xb, const uint32_t* table) {
     uint64_t sb, cb;
     const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);  // the caller has checked is_stashed(xb)
     if (a.sin_out) a.sin_out[idx] = __longlong_as_double((long long)sb);
@@ -509,8 +517,8 @@ __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t
     if (a.k_out) a.k_out[idx] = q;
 }
 
-__device__ __forceinline__ void stage_table(uint64_t* table) {
-    if (threadIdx.x < FABE13_PH_WORDS) table[threadIdx.x] = c_ph_table[threadIdx.x];
+__device__ __forceinline__ void stage_table(uint32_t* table) {
+    if (threadIdx.x < FABE13_PH_STREAM_WORDS) table[threadIdx.x] = c_ph_stream[threadIdx.x];
     __syncthreads();
 }
 
@@ -521,7 +529,7 @@ __device__ __forceinline__ void stage_table(uint64_t* table) {
 // one slot they read the same x and write the same bits.
 template <int CORE>
 __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const SecondPassArgs a) {
-    __shared__ uint64_t table[FABE13_PH_WORDS];
+    __shared__ uint32_t table[FABE13_PH_STREAM_WORDS];
     __shared__ uint32_t seg_start[kSegments + 1];
     __shared__ int overflowed;
     grid_dependency_wait();  // everything below reads what the stream kernel wrote
@@ -585,7 +593,7 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
 template <int CORE>
 __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* in, double* sin_out, double* cos_out,
                                                                   long long* k_out, uint32_t n) {
-    __shared__ uint64_t table[FABE13_PH_WORDS];
+    __shared__ uint32_t table[FABE13_PH_STREAM_WORDS];
     stage_table(table);
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const uint64_t xb = (uint64_t)__double_as_longlong(in[i]);

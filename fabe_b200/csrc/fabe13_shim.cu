@@ -33,7 +33,7 @@ constexpr int kSlots = 8;                                  // pipeline depth of 
 constexpr size_t kLaunchMaxElems = (size_t)1 << 30;        // per launch sequence; keeps 32-bit indices and alignment
 constexpr size_t kZeroCopyPageableMax = 32768;             // pageable callers: bounce through one small pinned block
 
-const uint64_t h_ph_table[FABE13_PH_WORDS] = FABE13_PH_TABLE;
+const uint32_t h_ph_stream[FABE13_PH_STREAM_WORDS] = FABE13_PH_STREAM;
 
 // ---------------------------------------------------------------------------------------------------------------
 // configuration (reference: compile-time constants fabe13/fabe13.c:71-73; here run-time options)
@@ -524,9 +524,9 @@ void host_one(double x, int core, double* s, double* c, long long* k) {
     uint64_t sb, cb;
     int64_t kk;
     if (core == FABE13_CORE_PSI)
-        fabe13_sincos_one<FABE13_CORE_PSI>(fabe13_bits(x), h_ph_table, &sb, &cb, &kk);
+        fabe13_sincos_one<FABE13_CORE_PSI>(fabe13_bits(x), h_ph_stream, &sb, &cb, &kk);
     else
-        fabe13_sincos_one<FABE13_CORE_POLY>(fabe13_bits(x), h_ph_table, &sb, &cb, &kk);
+        fabe13_sincos_one<FABE13_CORE_POLY>(fabe13_bits(x), h_ph_stream, &sb, &cb, &kk);
     *s = fabe13_from_bits(sb);
     *c = fabe13_from_bits(cb);
     if (k) *k = (long long)kk;
