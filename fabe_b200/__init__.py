@@ -7,14 +7,19 @@ from ._lib import Fabe13Error  # noqa: F401
 from .api import (  # noqa: F401
     CORE_POLY,
     CORE_PSI,
+    OP_COT,
+    OP_SINC,
+    OP_TAN,
     PinnedArray,
     cos,
     cos_array,
     cot,
+    cot_array,
     fill_loguniform_device,
     fill_uniform_device,
     get_option,
     host_core,
+    host_derived,
     implementation_name,
     set_option,
     shard_bounds,
@@ -22,8 +27,10 @@ from .api import (  # noqa: F401
     sin,
     sin_array,
     sinc,
+    sinc_array,
     sincos,
     sincos_k,
     sincos_legacy,
     tan,
+    tan_array,
 )

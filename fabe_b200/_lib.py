@@ -38,12 +38,20 @@ def signatures():
         "fabe13_cos_device": (c.c_int, [_vp, _vp, c.c_size_t, _vp]),
         "fabe13_sin_host": (c.c_int, [_vp, _vp, c.c_size_t]),
         "fabe13_cos_host": (c.c_int, [_vp, _vp, c.c_size_t]),
+        "fabe13_tan_device": (c.c_int, [_vp, _vp, c.c_size_t, _vp]),
+        "fabe13_cot_device": (c.c_int, [_vp, _vp, c.c_size_t, _vp]),
+        "fabe13_sinc_device": (c.c_int, [_vp, _vp, c.c_size_t, _vp]),
+        "fabe13_tan_host": (c.c_int, [_vp, _vp, c.c_size_t]),
+        "fabe13_cot_host": (c.c_int, [_vp, _vp, c.c_size_t]),
+        "fabe13_sinc_host": (c.c_int, [_vp, _vp, c.c_size_t]),
         "fabe13_sincos_workspace_bytes": (c.c_size_t, [c.c_size_t]),
         "fabe13_sincos_device_ws": (c.c_int, [_vp, _vp, _vp, c.c_size_t, _vp, c.c_size_t, _vp]),
         "fabe13_sincos_multi": (c.c_int, [c.c_int, _vp, _vp, _vp, _vp, _vp]),
         "fabe13_sincos_host": (c.c_int, [_vp, _vp, _vp, c.c_size_t]),
         "fabe13_cuda_host_alloc": (_vp, [c.c_size_t]),
         "fabe13_cuda_host_free": (None, [_vp]),
+        "fabe13_cuda_host_register": (c.c_int, [_vp, c.c_size_t]),
+        "fabe13_cuda_host_unregister": (c.c_int, [_vp]),
         "fabe13_shard_bounds": (None, [c.c_size_t, c.c_int, c.c_int, c.POINTER(c.c_size_t), c.POINTER(c.c_size_t)]),
         "fabe13_cuda_set_option": (c.c_int, [c.c_char_p, c.c_longlong]),
         "fabe13_cuda_get_option": (c.c_int, [c.c_char_p, c.POINTER(c.c_longlong)]),
@@ -52,6 +60,7 @@ def signatures():
         "fabe13_cuda_last_error_string": (c.c_char_p, []),
         "fabe13_cuda_clear_error": (None, []),
         "fabe13_debug_host_core": (None, [_vp, _vp, _vp, _vp, c.c_size_t, c.c_int]),
+        "fabe13_debug_host_derived": (None, [_vp, _vp, c.c_size_t, c.c_int, c.c_int]),
         "fabe13_debug_fill_uniform_device": (c.c_int, [_vp, c.c_size_t, c.c_uint64, c.c_uint64, c.c_double, c.c_double, _vp]),
         "fabe13_debug_fill_loguniform_device": (c.c_int, [_vp, c.c_size_t, c.c_uint64, c.c_uint64, _vp]),
     }

@@ -97,6 +97,24 @@ def cos_array(x, out=None):
     return _single(x, out, "fabe13_cos_device", "fabe13_cos_host", "fabe13_cos")
 
 
+def tan_array(x, out=None):
+    """tan(x) element-wise (array form of fabe13_tan: sin/cos, NaN where cos == 0)."""
+    return _single(x, out, "fabe13_tan_device", "fabe13_tan_host", "fabe13_tan")
+
+
+def cot_array(x, out=None):
+    """cot(x) element-wise (array form of fabe13_cot: cos/sin, NaN where sin == 0)."""
+    return _single(x, out, "fabe13_cot_device", "fabe13_cot_host", "fabe13_cot")
+
+
+def sinc_array(x, out=None):
+    """sinc(x) = sin(x)/x element-wise, 1 for |x| < 1e-9 (array form of fabe13_sinc)."""
+    return _single(x, out, "fabe13_sinc_device", "fabe13_sinc_host", "fabe13_sinc")
+
+
+OP_TAN, OP_COT, OP_SINC = 3, 4, 5
+
+
 def sincos_k(x):
     """(sin, cos, k) for a torch CUDA float64 tensor; k is the reference's quadrant index (test hook)."""
     import torch
@@ -221,6 +239,15 @@ def fill_loguniform_device(t, seed, first_index=0):
         rc = lib.fabe13_debug_fill_loguniform_device(t.data_ptr(), t.numel(), seed, first_index, st)
     _lib.check(rc, "fabe13_debug_fill_loguniform_device")
     return t
+
+
+def host_derived(x, op, core=CORE_POLY):
+    """Test hook: tan / cot / sinc (op = OP_TAN / OP_COT / OP_SINC) evaluated by the shared core on the host."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib.fabe13_debug_host_derived(x.ctypes.data, out.ctypes.data, x.size, op, core)
+    return out
 
 
 def host_core(x, core=CORE_POLY):

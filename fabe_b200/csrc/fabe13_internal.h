@@ -33,9 +33,10 @@ size_t workspace_bytes(size_t n, const LaunchTuning& t);
 
 // Enqueue the sincos path for n <= 2^31 elements on `stream`.  `workspace` must hold workspace_bytes(n) bytes
 // (it is zero-initialised here, on the stream).  d_k may be null.  One of d_sin / d_cos may be null: then only the
-// other output is produced (16 B/element instead of 24).  Returns the number of kernels launched via
+// other output is produced (16 B/element instead of 24).  op = 0 (FABE13_OP_SINCOS) for these; FABE13_OP_TAN / _COT /
+// _SINC write that function of the pair to d_sin (d_cos and d_k null).  Returns the number of kernels launched via
 // *launches.  Every pointer is a device pointer on the current device.
-cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int core,
+cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int op, int core,
                           const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                           int* launches);
 

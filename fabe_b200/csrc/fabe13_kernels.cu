@@ -70,7 +70,11 @@ struct Worklist {
 };
 
 // which outputs a launch produces: both (the reference's fabe13_sincos), or one of them (16 B/element)
-enum { OUT_BOTH = 0, OUT_SIN = 1, OUT_COS = 2 };
+// (or a derived function of the pair -- tan, cot, sinc -- written to the first output array; fused kernel only)
+enum { OUT_BOTH = 0, OUT_SIN = 1, OUT_COS = 2, OUT_TAN = FABE13_OP_TAN, OUT_COT = FABE13_OP_COT, OUT_SINC = FABE13_OP_SINC };
+__host__ __device__ constexpr bool out_first(int out) { return out != OUT_COS; }                    // writes sin_out
+__host__ __device__ constexpr bool out_second(int out) { return out == OUT_BOTH || out == OUT_COS; }  // writes cos_out
+__host__ __device__ constexpr bool out_derived(int out) { return out >= OUT_TAN; }
 
 struct StreamArgs {
     const double* in;
@@ -135,8 +139,16 @@ __device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& c
     const double r = fabe13_cody_waite(x, kd);
     double sr, cr;
     fabe13_core<CORE>(r, &sr, &cr);
-    fabe13_fixup<(OUT == OUT_COS) ? FABE13_STASH_COS : FABE13_STASH_SIN>(xb, sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
     const uint32_t ahi = fabe13_abs_hi(xb);
+    if (out_derived(OUT)) {
+        // complete fix-up (tiny -> (x, 1), NaN/Inf -> qNaN), the division, then park x for the Payne-Hanek pass
+        uint64_t s0, c0;
+        fabe13_fixup<FABE13_STASH_NONE>(xb, sr, cr, fabe13_q_from_biased(biased), &s0, &c0);
+        sb = fabe13_is_huge(ahi) ? xb : fabe13_derived<OUT>(xb, s0, c0);
+        cb = 0;
+    } else {
+        fabe13_fixup<(OUT == OUT_COS) ? FABE13_STASH_COS : FABE13_STASH_SIN>(xb, sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
+    }
     if (WITH_K) k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
     return fabe13_is_plain(ahi);
 }
@@ -165,8 +177,8 @@ template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
 __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const double* in = a.in + a.head;
-    double* so = (OUT != OUT_COS) ? a.sin_out + a.head : nullptr;
-    double* co = (OUT != OUT_SIN) ? a.cos_out + a.head : nullptr;
+    double* so = out_first(OUT) ? a.sin_out + a.head : nullptr;
+    double* co = out_second(OUT) ? a.cos_out + a.head : nullptr;
 
     // grid-stride over chunks of tiles_per_block consecutive tiles; trip counts are block-uniform, so the ballots
     // below always see full warps
@@ -199,8 +211,8 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
             for (int u = 0; u < UNROLL; ++u) {
                 if (live[u]) {
                     const size_t e = (size_t)(v0 + u * kThreads) * VEC;
-                    if (OUT != OUT_COS) store_stream<VEC>(so + e, sb[u]);
-                    if (OUT != OUT_SIN) store_stream<VEC>(co + e, cb[u]);
+                    if (out_first(OUT)) store_stream<VEC>(so + e, sb[u]);
+                    if (out_second(OUT)) store_stream<VEC>(co + e, cb[u]);
                     if (WITH_K) {
 #pragma unroll
                         for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
@@ -245,8 +257,8 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
         fast_lane<CORE, WITH_K, OUT>(xb, sb, cb, k);
         const bool huge = is_stashed(xb);
         if (on) {
-            if (OUT != OUT_COS) a.sin_out[idx] = __longlong_as_double((long long)sb);
-            if (OUT != OUT_SIN) a.cos_out[idx] = __longlong_as_double((long long)cb);
+            if (out_first(OUT)) a.sin_out[idx] = __longlong_as_double((long long)sb);
+            if (out_second(OUT)) a.cos_out[idx] = __longlong_as_double((long long)cb);
             if (WITH_K) a.k_out[idx] = k;
         }
         worklist_push(huge ? 1u : 0u, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
@@ -286,8 +298,9 @@ template <int CORE, int OUT>
 __device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64_t xb, const uint32_t* table) {
     uint64_t sb, cb;
     const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);
-    if (OUT != OUT_COS) a.sin_out[e] = __longlong_as_double((long long)sb);
-    if (OUT != OUT_SIN) a.cos_out[e] = __longlong_as_double((long long)cb);
+    if (out_derived(OUT)) sb = fabe13_derived<OUT>(xb, sb, cb);
+    if (out_first(OUT)) a.sin_out[e] = __longlong_as_double((long long)sb);
+    if (out_second(OUT)) a.cos_out[e] = __longlong_as_double((long long)cb);
     if (a.k_out) a.k_out[e] = q;
 }
 
@@ -318,9 +331,11 @@ __device__ __noinline__ void dense_rounds(long long* k_out, uint32_t head, uint3
     for (uint32_t r = 0; r < (uint32_t)(UNROLL * VEC); ++r) {
         uint64_t s1, c1;
         int64_t k;
-        fabe13_sincos_one<CORE>(sh.x[warp][r * 32 + lane], sh.table[warp], &s1, &c1, &k);
+        const uint64_t xr = sh.x[warp][r * 32 + lane];
+        fabe13_sincos_one<CORE>(xr, sh.table[warp], &s1, &c1, &k);
+        if (out_derived(OUT)) s1 = fabe13_derived<OUT>(xr, s1, c1);
         sh.x[warp][r * 32 + lane] = s1;
-        sh.c[warp][r * 32 + lane] = c1;
+        if (out_second(OUT)) sh.c[warp][r * 32 + lane] = c1;
         if (WITH_K) {
             const uint32_t v = v0 + (r / VEC) * kThreads;
             if (v < nvec) k_out[head + (size_t)v * VEC + r % VEC] = k;
@@ -336,8 +351,8 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     const double* in = a.in + a.head;
-    double* so = (OUT != OUT_COS) ? a.sin_out + a.head : nullptr;
-    double* co = (OUT != OUT_SIN) ? a.cos_out + a.head : nullptr;
+    double* so = out_first(OUT) ? a.sin_out + a.head : nullptr;
+    double* co = out_second(OUT) ? a.cos_out + a.head : nullptr;
     auto& s_x = sh.x;
     auto& s_off = sh.off;
     auto& s_table = sh.table;
@@ -381,7 +396,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 sb[u][j] = s_x[warp][(u * VEC + j) * 32 + lane];
-                cb[u][j] = sh.c[warp][(u * VEC + j) * 32 + lane];
+                cb[u][j] = out_second(OUT) ? sh.c[warp][(u * VEC + j) * 32 + lane] : 0;
             }
         }
         __syncwarp();  // the slice is reused by the warp's next tile
@@ -397,8 +412,8 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
     for (int u = 0; u < UNROLL; ++u) {
         if (live[u]) {
             const size_t e = (size_t)(v0 + u * kThreads) * VEC;
-            if (OUT != OUT_COS) store_stream<VEC>(so + e, sb[u]);
-            if (OUT != OUT_SIN) store_stream<VEC>(co + e, cb[u]);
+            if (out_first(OUT)) store_stream<VEC>(so + e, sb[u]);
+            if (out_second(OUT)) store_stream<VEC>(co + e, cb[u]);
             if (WITH_K && !dense) {  // (the dense route has written its k values itself)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
@@ -493,8 +508,9 @@ __global__ void __launch_bounds__(kThreads, CORE == FABE13_CORE_PSI ? 4 : FABE13
             uint64_t sb, cb;
             int64_t k;
             fabe13_sincos_one<CORE>(xb, c_ph_stream, &sb, &cb, &k);
-            if (OUT != OUT_COS) a.sin_out[idx] = __longlong_as_double((long long)sb);
-            if (OUT != OUT_SIN) a.cos_out[idx] = __longlong_as_double((long long)cb);
+            if (out_derived(OUT)) sb = fabe13_derived<OUT>(xb, sb, cb);
+            if (out_first(OUT)) a.sin_out[idx] = __longlong_as_double((long long)sb);
+            if (out_second(OUT)) a.cos_out[idx] = __longlong_as_double((long long)cb);
             if (WITH_K) a.k_out[idx] = k;
         }
     }
@@ -505,6 +521,7 @@ struct SecondPassArgs {
     double* cos_out;
     long long* k_out;
     uint32_t n;
+    int op;            // FABE13_OP_SINCOS, or the derived function whose values go to sin_out
     Worklist wl;
 };
 
@@ -512,6 +529,7 @@ template <int CORE>
 __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t idx, uint64_t xb, const uint32_t* table) {
     uint64_t sb, cb;
     const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);  // the caller has checked is_stashed(xb)
+    if (a.op != FABE13_OP_SINCOS) sb = fabe13_derived_rt(a.op, xb, sb, cb);
     if (a.sin_out) a.sin_out[idx] = __longlong_as_double((long long)sb);
     if (a.cos_out) a.cos_out[idx] = __longlong_as_double((long long)cb);
     if (a.k_out) a.k_out[idx] = q;
@@ -592,7 +610,7 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
 // Small n: launch latency is everything, so one kernel does every path inline.
 template <int CORE>
 __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* in, double* sin_out, double* cos_out,
-                                                                  long long* k_out, uint32_t n) {
+                                                                  long long* k_out, uint32_t n, int op) {
     __shared__ uint32_t table[FABE13_PH_STREAM_WORDS];
     stage_table(table);
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -600,6 +618,7 @@ __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* i
         uint64_t sb, cb;
         int64_t k;
         fabe13_sincos_one<CORE>(xb, table, &sb, &cb, &k);
+        if (op != FABE13_OP_SINCOS) sb = fabe13_derived_rt(op, xb, sb, cb);
         if (sin_out) sin_out[i] = __longlong_as_double((long long)sb);
         if (cos_out) cos_out[i] = __longlong_as_double((long long)cb);
         if (k_out) k_out[i] = k;
@@ -670,8 +689,24 @@ cudaError_t launch_stream_vec(const StreamArgs& a, bool fused, int vec, int unro
     }
 }
 
+template <int CORE, int OUT>
+cudaError_t launch_stream_unroll_derived(const StreamArgs& a, int vec, int grid, cudaStream_t stream) {
+    const bool one_tile = (uint32_t)grid == a.ntiles && a.tiles_per_block == 1;
+#define FABE13_LAUNCH_DERIVED(V)                                                                                         \
+    return one_tile ? launch_1arg(sincos_fused_kernel<CORE, V, 1, false, OUT, true>, a, grid, kThreads, stream, a.pdl)   \
+                    : launch_1arg(sincos_fused_kernel<CORE, V, 1, false, OUT, false>, a, grid, kThreads, stream, a.pdl)
+    if (vec == 4) FABE13_LAUNCH_DERIVED(4);
+    if (vec == 2) FABE13_LAUNCH_DERIVED(2);
+    FABE13_LAUNCH_DERIVED(1);
+#undef FABE13_LAUNCH_DERIVED
+}
+
 template <int CORE>
-cudaError_t launch_stream(const StreamArgs& a, bool fused, int vec, int unroll, int grid, cudaStream_t stream) {
+cudaError_t launch_stream(const StreamArgs& a, int op, bool fused, int vec, int unroll, int grid, cudaStream_t stream) {
+    // derived functions: fused kernel only, one vector in flight per thread (unroll 1)
+    if (op == FABE13_OP_TAN) return launch_stream_unroll_derived<CORE, OUT_TAN>(a, vec, grid, stream);
+    if (op == FABE13_OP_COT) return launch_stream_unroll_derived<CORE, OUT_COT>(a, vec, grid, stream);
+    if (op == FABE13_OP_SINC) return launch_stream_unroll_derived<CORE, OUT_SINC>(a, vec, grid, stream);
     if (a.sin_out && a.cos_out)
         return a.k_out ? launch_stream_vec<CORE, true, OUT_BOTH>(a, fused, vec, unroll, grid, stream)
                        : launch_stream_vec<CORE, false, OUT_BOTH>(a, fused, vec, unroll, grid, stream);
@@ -696,16 +731,17 @@ uint32_t segment_capacity(size_t n, const LaunchTuning& t, int mode) {
 }
 
 template <int CORE>
-cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
+cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int op,
                         const LaunchTuning& t, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                         int* launches) {
     int mode = worklist_mode(n, t);
+    if (op != FABE13_OP_SINCOS && mode == WL_GLOBAL) mode = WL_HYBRID;  // derived functions exist in the fused kernel only
     if (mode != WL_LOCAL && workspace == nullptr) mode = WL_LOCAL;  // no scratch: everything stays in the block
     const bool fused = mode != WL_GLOBAL;
     if (n < (size_t)t.small_n) {
         const long long need = (long long)((n + kThreads - 1) / kThreads);
         const long long cap = (long long)dev.sm_count * 64;
-        sincos_inline_kernel<CORE><<<(int)(need < cap ? need : cap), kThreads, 0, stream>>>(d_in, d_sin, d_cos, d_k, (uint32_t)n);
+        sincos_inline_kernel<CORE><<<(int)(need < cap ? need : cap), kThreads, 0, stream>>>(d_in, d_sin, d_cos, d_k, (uint32_t)n, op);
         *launches += 1;
         return cudaGetLastError();
     }
@@ -748,7 +784,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
         a.wl.seg_cap = 0;
         a.pdl = false;
         *launches += 1;
-        return launch_stream<CORE>(a, true, vec, unroll, (int)grid, stream);
+        return launch_stream<CORE>(a, op, true, vec, unroll, (int)grid, stream);
     }
 
     // global or hybrid: zero the counters -> streaming kernel -> second pass over the global worklist
@@ -765,7 +801,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
         err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
     }
     if (err != cudaSuccess) return err;
-    err = launch_stream<CORE>(a, fused, vec, unroll, (int)grid, stream);
+    err = launch_stream<CORE>(a, op, fused, vec, unroll, (int)grid, stream);
     if (err != cudaSuccess) return err;
 
     SecondPassArgs b;
@@ -773,6 +809,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     b.cos_out = d_cos;
     b.k_out = d_k;
     b.n = (uint32_t)n;
+    b.op = op;
     b.wl = a.wl;
     err = launch_1arg(sincos_second_pass_kernel<CORE>, b, dev.sm_count * t.second_pass_blocks_per_sm, kThreads, stream, a.pdl);
     *launches += a.pdl ? 3 : 2;
@@ -801,14 +838,15 @@ cudaError_t fill_loguniform(double* d_out, size_t n, uint64_t seed, uint64_t fir
     return cudaGetLastError();
 }
 
-cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int core,
+cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, int op, int core,
                           const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                           int* launches) {
     if (n == 0) return cudaSuccess;
     if (n > ((size_t)1 << 31) || (!d_sin && !d_cos)) return cudaErrorInvalidValue;
+    if (op != FABE13_OP_SINCOS && (op < FABE13_OP_TAN || op > FABE13_OP_SINC || !d_sin || d_cos || d_k)) return cudaErrorInvalidValue;
     if (core == FABE13_CORE_PSI)
-        return launch_core<FABE13_CORE_PSI>(d_in, d_sin, d_cos, d_k, n, tuning, dev, workspace, stream, launches);
-    return launch_core<FABE13_CORE_POLY>(d_in, d_sin, d_cos, d_k, n, tuning, dev, workspace, stream, launches);
+        return launch_core<FABE13_CORE_PSI>(d_in, d_sin, d_cos, d_k, n, op, tuning, dev, workspace, stream, launches);
+    return launch_core<FABE13_CORE_POLY>(d_in, d_sin, d_cos, d_k, n, op, tuning, dev, workspace, stream, launches);
 }
 
 }  // namespace fabe13

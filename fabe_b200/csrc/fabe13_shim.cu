@@ -47,7 +47,7 @@ struct Config {
     std::atomic<long long> pdl{1};
     std::atomic<long long> second_pass_blocks_per_sm{8};
     std::atomic<long long> unroll{1};
-    std::atomic<long long> small_n{(long long)1 << 22};
+    std::atomic<long long> small_n{(long long)1 << 20};
     std::atomic<long long> worklist_shift{3};
     std::atomic<long long> chunk_elems{(long long)1 << 22};
     std::atomic<long long> host_devices{1};
@@ -200,7 +200,7 @@ int current_device_state(DeviceState** out) {
 // device-pointer path
 // ---------------------------------------------------------------------------------------------------------------
 int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n, void* user_ws,
-               size_t user_ws_bytes, cudaStream_t stream) {
+               size_t user_ws_bytes, cudaStream_t stream, int op = FABE13_OP_SINCOS) {
     if (n == 0) return 0;
     DeviceState* ds;
     if (int rc = current_device_state(&ds)) return rc;
@@ -222,7 +222,7 @@ int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k,
         }
         int launches = 0;
         cudaError_t e = fabe13::launch_sincos(d_in + off, d_sin ? d_sin + off : nullptr, d_cos ? d_cos + off : nullptr,
-                                              d_k ? d_k + off : nullptr, m, core, t, ds->info, ws, stream, &launches);
+                                              d_k ? d_k + off : nullptr, m, op, core, t, ds->info, ws, stream, &launches);
         g_launches.fetch_add((unsigned long long)launches);
         if (pooled) {
             cudaError_t e2 = cudaFreeAsync(ws, stream);
@@ -320,10 +320,10 @@ size_t pick_chunk(size_t n) {
 
 // enqueue one chunk on a slot: H2D, kernels, 2x D2H.  src/dst are pinned (user memory or staging).
 int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, double* dst_cos, size_t m,
-                  const LaunchTuning& t, int core) {
+                  const LaunchTuning& t, int core, int op) {
     FABE13_TRY(cudaMemcpyAsync(sl.d_in, src, m * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
     int launches = 0;
-    cudaError_t e = fabe13::launch_sincos(sl.d_in, dst_sin ? sl.d_sin : nullptr, dst_cos ? sl.d_cos : nullptr, nullptr, m, core,
+    cudaError_t e = fabe13::launch_sincos(sl.d_in, dst_sin ? sl.d_sin : nullptr, dst_cos ? sl.d_cos : nullptr, nullptr, m, op, core,
                                           t, s.info, (m >= (size_t)t.small_n && fabe13::workspace_bytes(m, t) > 0) ? sl.d_ws : nullptr, sl.stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
     if (e != cudaSuccess) return record(e, "launch_sincos(host path)");
@@ -337,7 +337,7 @@ int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, 
 // launch for small n.  Small pageable calls are bounced through a pinned staging block.  Returns -1 if this route is not available
 // (memory registered without a device mapping), in which case the caller takes the copy pipeline.
 int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned,
-               const LaunchTuning& t, int core) {
+               const LaunchTuning& t, int core, int op) {
     if (!s.small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&s.small_stream, cudaStreamNonBlocking));
     const double* src = in;
     double *dst_s = sin_out, *dst_c = cos_out;  // either may be null (single-output calls)
@@ -367,7 +367,7 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
     const size_t need_ws = n >= (size_t)t.small_n ? fabe13::workspace_bytes(n, t) : 0;
     if (need_ws > 0)  // a global worklist is in play: the launch sequence needs its scratch
         FABE13_TRY(cudaMallocFromPoolAsync(&ws, need_ws, s.pool, s.small_stream));
-    cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, core, t, s.info, ws,
+    cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, op, core, t, s.info, ws,
                                           s.small_stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
     if (ws) {
@@ -384,7 +384,7 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
 }
 
 // One device, one contiguous slice.  Caller has made `dev` current.
-int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned) {
+int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned, int op) {
     DeviceState* ds;
     if (int rc = device_state(dev, &ds)) return rc;
     std::lock_guard<std::mutex> lk(ds->pipe_mu);
@@ -394,7 +394,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     // copy pipeline up to ~1e7 elements, measured), small calls only for pageable ones (they need a bounce buffer)
     const size_t zc_max = (size_t)g_cfg.zero_copy_max.load();
     if (n <= (pinned ? zc_max : (zc_max < kZeroCopyPageableMax ? zc_max : kZeroCopyPageableMax))) {
-        const int rc = host_small(*ds, in, sin_out, cos_out, n, pinned, t, core);
+        const int rc = host_small(*ds, in, sin_out, cos_out, n, pinned, t, core, op);
         if (rc >= 0) return rc;
     }
     size_t chunk = pick_chunk(n);
@@ -408,7 +408,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
             if (int rc = enqueue_chunk(*ds, ds->slots[i % kSlots], in + off, sin_out ? sin_out + off : nullptr,
-                                       cos_out ? cos_out + off : nullptr, m, t, core))
+                                       cos_out ? cos_out + off : nullptr, m, t, core, op))
                 return rc;
         }
         if (n >= ((size_t)1 << 22)) {
@@ -440,7 +440,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
             memcpy(sl.h_in, in + off, m * sizeof(double));
-            int rc = enqueue_chunk(*ds, sl, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core);
+            int rc = enqueue_chunk(*ds, sl, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core, op);
             if (rc == 0) {
                 cudaError_t e;
                 if (n >= ((size_t)1 << 22)) {  // long waits: sleep on a blocking event; short ones: spin (lower latency)
@@ -470,7 +470,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     return rc_all.load();
 }
 
-int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
+int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int op = FABE13_OP_SINCOS) {
     if (n == 0) return 0;
     load_env();
     if (!sin_out && !cos_out) return record(cudaErrorInvalidValue, "no output array");
@@ -480,7 +480,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
     if (ki == PTR_DEVICE || ks == PTR_DEVICE || kc == PTR_DEVICE) {
         if (!(ki == PTR_DEVICE && ks == PTR_DEVICE && kc == PTR_DEVICE))
             return record(cudaErrorInvalidValue, "fabe13_sincos: mixed host and device pointers");
-        if (int rc = run_device(in, sin_out, cos_out, nullptr, n, nullptr, 0, nullptr)) return rc;
+        if (int rc = run_device(in, sin_out, cos_out, nullptr, n, nullptr, 0, nullptr, op)) return rc;
         FABE13_TRY(cudaStreamSynchronize(nullptr));
         return 0;
     }
@@ -491,7 +491,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
     FABE13_TRY(cudaGetDeviceCount(&ndev_avail));
     int ndev = (int)g_cfg.host_devices.load();
     if (ndev > ndev_avail) ndev = ndev_avail;
-    if (ndev <= 1 || n < ((size_t)1 << 20)) return host_slice(cur, in, sin_out, cos_out, n, pinned);
+    if (ndev <= 1 || n < ((size_t)1 << 20)) return host_slice(cur, in, sin_out, cos_out, n, pinned, op);
 
     // contiguous slice per GPU, one host thread each; no exchange between slices
     std::vector<std::thread> th;
@@ -506,7 +506,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n) {
                 return;
             }
             if (e > b)
-                rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned);
+                rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned, op);
         });
     }
     for (std::thread& x : th) x.join();
@@ -530,6 +530,24 @@ void host_one(double x, int core, double* s, double* c, long long* k) {
     *s = fabe13_from_bits(sb);
     *c = fabe13_from_bits(cb);
     if (k) *k = (long long)kk;
+}
+
+template <int OP>
+double host_derived(double x) {
+    double s, c;
+    host_one(x, cfg_core(), &s, &c, nullptr);
+    return fabe13_from_bits(fabe13_derived<OP>(fabe13_bits(x), fabe13_bits(s), fabe13_bits(c)));
+}
+
+int derived_device(const double* d_in, double* d_out, size_t n, void* cuda_stream, int op, const char* who) {
+    if (!d_out && n) return record(cudaErrorInvalidValue, who);
+    return run_device(d_in, d_out, nullptr, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream, op);
+}
+
+int derived_host(const double* in, double* out, size_t n, int op, const char* who) {
+    if (n == 0) return 0;
+    if (!out) return record(cudaErrorInvalidValue, who);
+    return run_host(in, out, nullptr, n, op);
 }
 
 }  // namespace
@@ -572,24 +590,11 @@ double fabe13_cos(double x) {
     host_one(x, cfg_core(), &s, &c, nullptr);
     return c;
 }
-double fabe13_sinc(double x) {
-    if (fabs(x) < 1e-9) return 1.0;
-    double s, c;
-    host_one(x, cfg_core(), &s, &c, nullptr);
-    return s / x;
-}
-double fabe13_tan(double x) {
-    double s, c;
-    host_one(x, cfg_core(), &s, &c, nullptr);
-    if (c == 0.0) return NAN;
-    return s / c;
-}
-double fabe13_cot(double x) {
-    double s, c;
-    host_one(x, cfg_core(), &s, &c, nullptr);
-    if (s == 0.0) return NAN;
-    return c / s;
-}
+// sinc / tan / cot: the reference's guards (fabe13/fabe13.c:264-266: |x| < 1e-9 -> 1, cos == 0 -> NAN, sin == 0 -> NAN)
+// around one division; the same fabe13_derived the array kernels compile for the device
+double fabe13_sinc(double x) { return host_derived<FABE13_OP_SINC>(x); }
+double fabe13_tan(double x) { return host_derived<FABE13_OP_TAN>(x); }
+double fabe13_cot(double x) { return host_derived<FABE13_OP_COT>(x); }
 double fabe13_atan(double x) { return atan(x); }
 double fabe13_asin(double x) { return asin(x); }
 double fabe13_acos(double x) { return acos(x); }
@@ -617,6 +622,20 @@ int fabe13_cos_host(const double* in, double* out, size_t n) {
     if (!out) return record(cudaErrorInvalidValue, "fabe13_cos_host: null output");
     return run_host(in, nullptr, out, n);
 }
+
+// array forms of fabe13_tan / fabe13_cot / fabe13_sinc: the same per-element code as the scalar entry points
+int fabe13_tan_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
+    return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_TAN, "fabe13_tan_device: null output");
+}
+int fabe13_cot_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
+    return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_COT, "fabe13_cot_device: null output");
+}
+int fabe13_sinc_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
+    return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_SINC, "fabe13_sinc_device: null output");
+}
+int fabe13_tan_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_TAN, "fabe13_tan_host: null output"); }
+int fabe13_cot_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_COT, "fabe13_cot_host: null output"); }
+int fabe13_sinc_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_SINC, "fabe13_sinc_host: null output"); }
 
 int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
                            void* cuda_stream) {
@@ -668,6 +687,17 @@ void* fabe13_cuda_host_alloc(size_t bytes) {
 
 void fabe13_cuda_host_free(void* p) {
     if (p) (void)cudaFreeHost(p);
+}
+
+int fabe13_cuda_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return record(cudaErrorInvalidValue, "fabe13_cuda_host_register");
+    FABE13_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return 0;
+}
+
+int fabe13_cuda_host_unregister(void* p) {
+    FABE13_TRY(cudaHostUnregister(p));
+    return 0;
 }
 
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end) {
@@ -733,6 +763,14 @@ void fabe13_cuda_clear_error(void) { g_last_error.store(0); }
 
 void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core) {
     for (size_t i = 0; i < n; ++i) host_one(in[i], core, &sin_out[i], &cos_out[i], k_out ? &k_out[i] : nullptr);
+}
+
+void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, int core) {
+    for (size_t i = 0; i < n; ++i) {
+        double s, c;
+        host_one(in[i], core, &s, &c, nullptr);
+        out[i] = fabe13_from_bits(fabe13_derived_rt(op, fabe13_bits(in[i]), fabe13_bits(s), fabe13_bits(c)));
+    }
 }
 
 int fabe13_debug_fill_uniform_device(double* d_out, size_t n, unsigned long long seed, unsigned long long first_index,

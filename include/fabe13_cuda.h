@@ -41,6 +41,17 @@ int fabe13_cos_device(const double* d_in, double* d_out, size_t n, void* cuda_st
 int fabe13_sin_host(const double* in, double* out, size_t n);
 int fabe13_cos_host(const double* in, double* out, size_t n);
 
+/* Array forms of fabe13_tan / fabe13_cot / fabe13_sinc (reference scalar API fabe13/fabe13.h:73-75, implementation
+ * fabe13/fabe13.c:264-266): tan = sin/cos (NaN if cos == 0), cot = cos/sin (NaN if sin == 0), sinc = 1 for
+ * |x| < 1e-9 and sin(x)/x otherwise -- one correctly rounded division after the sincos core, NaN results canonical.
+ * Element i equals the scalar entry point's value bit for bit.  One output array, 16 bytes of traffic per element. */
+int fabe13_tan_device(const double* d_in, double* d_out, size_t n, void* cuda_stream);
+int fabe13_cot_device(const double* d_in, double* d_out, size_t n, void* cuda_stream);
+int fabe13_sinc_device(const double* d_in, double* d_out, size_t n, void* cuda_stream);
+int fabe13_tan_host(const double* in, double* out, size_t n);
+int fabe13_cot_host(const double* in, double* out, size_t n);
+int fabe13_sinc_host(const double* in, double* out, size_t n);
+
 /* Same as fabe13_sincos_device with caller-provided scratch of at least fabe13_sincos_workspace_bytes(n) bytes
  * (no allocation on the call path; usable inside CUDA graph capture on any toolkit).  The size may be 0 (small n,
  * or option "worklist" = 2); a NULL workspace is accepted exactly then. */
@@ -65,6 +76,12 @@ int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_
 /* Pinned host allocations for the fast host path. */
 void* fabe13_cuda_host_alloc(size_t bytes);
 void fabe13_cuda_host_free(void* p);
+/* Opt-in for buffers the caller already owns (malloc, mmap, a language runtime's arrays): page-lock and map them once,
+ * and every later fabe13_sincos / _host call on them takes the pinned path (copy engines or zero-copy kernels reading
+ * and writing the caller's memory directly, no staging threads).  Registering costs about as much as one staged call
+ * over the same bytes, so it pays for buffers that are reused.  Thin wrappers over cudaHostRegister/Unregister. */
+int fabe13_cuda_host_register(void* p, size_t bytes);
+int fabe13_cuda_host_unregister(void* p);
 
 /* Contiguous slice [begin, end) of an n-element array owned by `rank` of `world` ranks; interior boundaries are
  * multiples of 4 elements so every slice keeps 32-byte alignment.  The remainder goes to the last rank. */
@@ -90,6 +107,8 @@ void fabe13_cuda_clear_error(void);
 /* Test hook, never on a product path: evaluates the shared per-element core on the HOST for n elements
  * (same code the kernels compile for the device).  Lets CPU-only CI check the algorithm without a GPU. */
 void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core);
+/* Same for the derived functions: op = 3 (tan), 4 (cot), 5 (sinc). */
+void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, int core);
 
 /* Bench/test hooks: fill a device array with the deterministic synthetic inputs used by bench.py and the parity
  * tests (counter-based splitmix64; the same generator exists on the host in oracle/fabe13_oracle.c).

@@ -43,7 +43,7 @@ def gpu_sincos(fabe13, cuda, x):
 # worklist + second-pass kernel alone (worklist=1), and the hybrid sequence forced at every size (worklist=3).  The
 # heaviest cases run in the default mode only; the tests of the global worklist's own machinery (capacity/overflow
 # rescan, PDL, caller workspace) are skipped where no global worklist exists.
-HEAVY = {"test_c3_1e9_properties", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
+HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
          "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
          "test_mixed_host_device_pointers_fail_loudly", "test_native_library_is_the_one_running"}
 GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
@@ -401,6 +401,28 @@ def test_host_pinned(fabe13, oracle, cuda, n):
         p.free()
 
 
+def test_registered_host_memory_takes_the_pinned_path(fabe13, oracle, cuda):
+    """fabe13_cuda_host_register: buffers the caller already owns are page-locked once; later calls on them are
+    classified as pinned (no staging threads) and give the same bits."""
+    lib = fabe13._lib.load()
+    n = 6_000_000
+    x = oracle.fill_uniform(n, 61, -1e4, 1e4)
+    x[::5000] = oracle.fill_loguniform(n // 5000, 62)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    want_s, want_c, _ = fabe13.host_core(x, 0)
+    for a in (x, s, c):
+        assert lib.fabe13_cuda_host_register(a.ctypes.data, a.nbytes) == 0
+    try:
+        fabe13.sincos(x, out_sin=s, out_cos=c)
+        assert np.array_equal(bits(s), bits(want_s)) and np.array_equal(bits(c), bits(want_c))
+    finally:
+        for a in (x, s, c):
+            assert lib.fabe13_cuda_host_unregister(a.ctypes.data) == 0
+    assert lib.fabe13_cuda_host_register(None, 16) != 0    # refused loudly
+    lib.fabe13_cuda_clear_error()
+
+
 def test_legacy_entry_point_int_n(fabe13, oracle, cuda):
     """void fabe13_sincos(const double*, double*, double*, int) -- reference fabe13/fabe13.h:51-56 -- with host
     pointers and with device pointers."""
@@ -549,6 +571,47 @@ def test_sin_only_cos_only_device(fabe13, cuda, oracle, small_n, core):
     fabe13.sin_array(y, out=y)
     torch.cuda.synchronize()
     assert torch.equal(y.view(torch.int64), s[3:].view(torch.int64))
+
+
+@pytest.mark.parametrize("small_n,core", [(0, 0), (0, 1), (1 << 30, 0)])
+def test_tan_cot_sinc_device(fabe13, cuda, oracle, small_n, core):
+    """Array forms of fabe13_tan / _cot / _sinc: every element equals the host instantiation (= the scalar API) bit for
+    bit, on plain, tiny, special and Payne-Hanek arguments, through every route of the fused kernel."""
+    import torch
+
+    fabe13.set_option("small_n", small_n)
+    fabe13.set_option("core", core)
+    n = 1_500_003
+    x = oracle.fill_uniform(n, 311, -1e5, 1e5)
+    x[::97] = oracle.fill_loguniform((n + 96) // 97, 312)              # sparse Payne-Hanek lanes
+    x[200_000:260_000] = oracle.fill_loguniform(60_000, 313)           # a dense stretch: dense-warp route
+    x[300_000:300_512:2] = 0.0                                         # tiny lanes, guards
+    x[5], x[6], x[7], x[8], x[9] = np.nan, np.inf, -0.0, 1e-300, 5e-10
+    xt = torch.from_numpy(x).to(cuda)
+    for op, fn in ((fabe13.OP_TAN, fabe13.tan_array), (fabe13.OP_COT, fabe13.cot_array), (fabe13.OP_SINC, fabe13.sinc_array)):
+        want = fabe13.host_derived(x, op, core)
+        got = fn(xt)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want)), f"op {op}"
+        y = xt[1:].clone()                                              # misaligned + in place
+        fn(y, out=y)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(y.cpu().numpy()), bits(want[1:])), f"op {op} in place"
+    ls, lc = oracle.libm(x)
+    body = np.isfinite(x) & (np.abs(x) > 1e-6)
+    t = fabe13.tan_array(xt).cpu().numpy()
+    assert (np.abs(t[body] - (ls / lc)[body]) / np.abs((ls / lc)[body])).max() < (1e-15 if core == 0 else 5e-15)  # psi core: 4.4e-16 per value
+
+
+@pytest.mark.parametrize("n", [7, 50_000, 3_000_000, 20_000_001])
+def test_tan_cot_sinc_host(fabe13, cuda, oracle, n):
+    x = oracle.fill_uniform(n, 314, -1e5, 1e5)
+    if n > 10:
+        x[3], x[4] = 1e300, 0.0
+    for op, fn in ((fabe13.OP_TAN, fabe13.tan_array), (fabe13.OP_COT, fabe13.cot_array), (fabe13.OP_SINC, fabe13.sinc_array)):
+        if n > 5_000_000 and op != fabe13.OP_TAN:
+            continue
+        assert np.array_equal(bits(fn(x)), bits(fabe13.host_derived(x, op))), f"op {op} n {n}"
 
 
 @pytest.mark.parametrize("n", [7, 50_000, 3_000_000])

@@ -125,3 +125,47 @@ def test_random_bit_patterns_host(fabe13, oracle):
         assert np.all(bits(s)[~fin] == np.uint64(0x7FF8000000000000)) and np.all(bits(c)[~fin] == np.uint64(0x7FF8000000000000))
         tiny = fin & (np.abs(x) <= 2.0 ** -27)
         assert np.array_equal(bits(s)[tiny], bits(x)[tiny]) and np.all(c[tiny] == 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# derived functions: tan, cot, sinc from one (sin, cos) pair and one division
+# ---------------------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def test_derived_functions_match_libm(fabe13, oracle):
+    x = np.concatenate([oracle.fill_uniform(200_000, 41, -1e4, 1e4), oracle.fill_uniform(50_000, 42, -3.2, 3.2),
+                        oracle.fill_loguniform(50_000, 43)])
+    ls, lc = oracle.libm(x)
+    t = fabe13.host_derived(x, fabe13.OP_TAN)
+    ct = fabe13.host_derived(x, fabe13.OP_COT)
+    sc = fabe13.host_derived(x, fabe13.OP_SINC)
+    # sin and cos are within 1 ulp each and the division rounds once: a few ulp of relative error, whatever |x|
+    assert _rel(t, ls / lc).max() < 1e-15
+    assert _rel(ct, lc / ls).max() < 1e-15
+    assert np.abs(sc - ls / x).max() < 2.3e-16 and _rel(sc[np.abs(x) < 1e8], (ls / x)[np.abs(x) < 1e8]).max() < 1e-15
+
+
+def test_derived_functions_guards_and_specials(fabe13):
+    qnan = np.uint64(0x7FF8000000000000)
+    x = np.array([0.0, -0.0, 5e-10, -9.9e-10, 1e-9, 2.0**-27, 1e-300, 5e-324, np.inf, -np.inf, np.nan, 1e308])
+    t = fabe13.host_derived(x, fabe13.OP_TAN)
+    ct = fabe13.host_derived(x, fabe13.OP_COT)
+    sc = fabe13.host_derived(x, fabe13.OP_SINC)
+    # reference guards (fabe13/fabe13.c:264-266): |x| < 1e-9 -> sinc = 1; sin == 0 -> cot = NaN; NaN/Inf in -> NaN out
+    assert np.all(sc[:4] == 1.0) and sc[4] == 1.0 and sc[5] == 1.0 and sc[6] == 1.0 and sc[7] == 1.0
+    assert bits(ct)[0] == qnan and bits(ct)[1] == qnan
+    assert ct[5] == 2.0**27 and ct[6] == 1.0 / 1e-300 and np.isinf(ct[7])        # cot(tiny) = 1/x, overflowing for subnormals
+    assert np.array_equal(bits(t[:8]), bits(x[:8]))                         # tan(tiny) = x bit for bit (+-0 included)
+    for arr in (t, ct, sc):
+        assert np.all(bits(arr)[8:11] == qnan)                              # canonical quiet NaN, sign/payload dropped
+    assert abs(t[11] - np.tan(1e308)) <= 4e-16 * abs(np.tan(1e308))
+
+
+def test_scalar_derived_api_is_the_array_code(fabe13, oracle):
+    x = np.concatenate([oracle.fill_uniform(300, 5, -50.0, 50.0), oracle.fill_loguniform(100, 6), [0.0, 1e-10, np.inf]])
+    for op, fn in ((fabe13.OP_TAN, fabe13.tan), (fabe13.OP_COT, fabe13.cot), (fabe13.OP_SINC, fabe13.sinc)):
+        want = fabe13.host_derived(x, op)
+        got = np.array([fn(v) for v in x])
+        assert np.array_equal(bits(got), bits(want))

@@ -62,7 +62,7 @@ def test_default_hot_kernel_uses_256_bit_accesses_and_does_not_spill(sass, core)
 
 def test_every_vec4_streaming_kernel_stores_vectors(sass):
     for name, body in pick(sass, r"sincos_(fused|stream)_kernelILi[01]ELi4E").items():
-        m = re.search(r"kernelILi[01]ELi4ELi([12])ELb[01]ELi([012])E", name)
+        m = re.search(r"kernelILi[01]ELi4ELi([12])ELb[01]ELi([0-5])E", name)
         unroll, out = int(m.group(1)), int(m.group(2))
         per_vector = 2 if out == 0 else 1
         assert count(body, r"STG\.E\.EF\S*\.256") == per_vector * unroll, name

@@ -13,10 +13,15 @@
 
 int main() {
     const size_t n = 600011, pad = 8;
-    std::vector<double> x(n), s(n + 2 * pad), c(n + 2 * pad), hs(n), hc(n);
+    std::vector<double> x(n), s(n + 2 * pad), c(n + 2 * pad), hs(n), hc(n), hd[3];
     for (size_t i = 0; i < n; ++i)
         x[i] = (i % 97 == 3) ? ldexp(1.0 + (i % 1000) / 1000.0, (int)(45 + i % 970)) : (i % 89 == 5 ? NAN : (double)i * 0.37 - 1e5);
+    for (size_t i = 200000; i < 260000; ++i) x[i] = ldexp(1.0 + (i % 1000) / 1000.0, (int)(45 + i % 970));  // dense-warp route
     fabe13_debug_host_core(x.data(), hs.data(), hc.data(), nullptr, n, 0);
+    for (int op = 3; op <= 5; ++op) {  // tan, cot, sinc
+        hd[op - 3].resize(n);
+        fabe13_debug_host_derived(x.data(), hd[op - 3].data(), n, op, 0);
+    }
     double *dx, *ds, *dc;
     cudaMalloc(&dx, (n + 2 * pad) * 8);
     cudaMalloc(&ds, (n + 2 * pad) * 8);
@@ -27,29 +32,34 @@ int main() {
     for (int off = 0; off < 4; ++off) {
         for (long long small : {0LL, 1LL << 30}) {
             fabe13_cuda_set_option("small_n", small);
-            for (long long shift : {3LL, 20LL}) {
-                fabe13_cuda_set_option("worklist_shift", shift);
-                for (int mode = 0; mode < 3; ++mode) {  // sincos, sin only, cos only
+            for (long long shift : {0LL, 1LL, 2LL, 3LL, 20LL}) {  // worklist designs 0..3; 20 = design 1 with a tiny list
+                fabe13_cuda_set_option("worklist", shift == 20 ? 1 : shift);
+                fabe13_cuda_set_option("worklist_shift", shift == 20 ? 20 : 3);
+                for (int mode = 0; mode < 6; ++mode) {  // sincos, sin only, cos only, tan, cot, sinc
                     cudaMemcpy(ds, g.data(), (n + 2 * pad) * 8, cudaMemcpyHostToDevice);
                     cudaMemcpy(dc, g.data(), (n + 2 * pad) * 8, cudaMemcpyHostToDevice);
                     cudaMemcpy(dx + off, x.data(), n * 8, cudaMemcpyHostToDevice);
                     int rc = mode == 0   ? fabe13_sincos_device(dx + off, ds + pad + off, dc + pad + off, n, nullptr)
                              : mode == 1 ? fabe13_sin_device(dx + off, ds + pad + off, n, nullptr)
-                                         : fabe13_cos_device(dx + off, dc + pad + off, n, nullptr);
+                             : mode == 2 ? fabe13_cos_device(dx + off, dc + pad + off, n, nullptr)
+                             : mode == 3 ? fabe13_tan_device(dx + off, ds + pad + off, n, nullptr)
+                             : mode == 4 ? fabe13_cot_device(dx + off, ds + pad + off, n, nullptr)
+                                         : fabe13_sinc_device(dx + off, ds + pad + off, n, nullptr);
                     cudaDeviceSynchronize();
                     cudaMemcpy(s.data(), ds, (n + 2 * pad) * 8, cudaMemcpyDeviceToHost);
                     cudaMemcpy(c.data(), dc, (n + 2 * pad) * 8, cudaMemcpyDeviceToHost);
                     int mism = 0, guards = 0;
                     for (size_t i = 0; i < n; ++i) {
-                        if (mode != 2 && memcmp(&s[pad + off + i], &hs[i], 8)) ++mism;
-                        if (mode != 1 && memcmp(&c[pad + off + i], &hc[i], 8)) ++mism;
+                        if (mode < 2 && memcmp(&s[pad + off + i], &hs[i], 8)) ++mism;
+                        if ((mode == 0 || mode == 2) && memcmp(&c[pad + off + i], &hc[i], 8)) ++mism;
+                        if (mode >= 3 && memcmp(&s[pad + off + i], &hd[mode - 3][i], 8)) ++mism;
                     }
                     for (size_t i = 0; i < n + 2 * pad; ++i) {
                         const bool inside = i >= pad + off && i < pad + off + n;
                         if ((!inside || mode == 2) && s[i] != guard) ++guards;
-                        if ((!inside || mode == 1) && c[i] != guard) ++guards;
+                        if ((!inside || mode == 1 || mode >= 3) && c[i] != guard) ++guards;
                     }
-                    printf("off %d small_n %lld shift %lld mode %d rc %d mismatches %d guard-hits %d\n", off, small, shift, mode, rc, mism, guards);
+                    printf("off %d small_n %lld worklist %lld mode %d rc %d mismatches %d guard-hits %d\n", off, small, shift, mode, rc, mism, guards);
                     bad += mism + guards + (rc != 0);
                 }
             }
