@@ -760,7 +760,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     const uintptr_t vbytes = (uintptr_t)vec * 8;
     uint32_t head = (uint32_t)(((vbytes - (pi & (vbytes - 1))) & (vbytes - 1)) / 8);
     if (head > n) head = (uint32_t)n;
-    const int unroll = t.unroll == 2 ? 2 : 1;
+    const int unroll = (t.unroll == 2 && op == FABE13_OP_SINCOS) ? 2 : 1;  // derived functions: unroll 1 only
 
     StreamArgs a;
     a.in = d_in;

@@ -17,4 +17,11 @@ python bench.py $SHORT --workload c4 > ${P}_plain_c4.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:sincos_fused -s 3 -c 1 -o ${P}_prof_fused_c4 \
       python bench.py $SHORT --workload c4 > ${P}_ncu_full_c4.log 2>&1
 python tools/run_all_configs.py > ${P}_all_configs.md 2> ${P}_all_configs.err
+python tools/derived_timing.py > ${P}_derived.md 2> ${P}_derived.err
+python tools/ab_worklist.py final 0,1 > ${P}_ab_worklist.txt 2>&1
+tools/abi_bench > ${P}_abi_bench.txt 2>&1
+tools/abi_selfcheck > ${P}_selfcheck.txt 2>&1
+python tools/soak.py 300 7 > ${P}_soak.txt 2>&1
+python tools/accuracy_report.py > ${P}_accuracy.txt 2>&1
+[ -x oracle/_ref/fabe13_test_runner_b200 ] && oracle/_ref/fabe13_test_runner_b200 > ${P}_ref_test_runner.txt 2>&1
 tail -c 600 ${P}_bench_c3.json

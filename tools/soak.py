@@ -46,12 +46,13 @@ def main():
         n = int(rng.choice([rng.integers(1, 100), rng.integers(100, 100_000), rng.integers(100_000, 6_000_000), rng.integers(4_000_000, 12_000_000)]))
         opts = {"small_n": int(rng.choice([0, 1 << 22, 1 << 30])), "worklist_shift": int(rng.choice([0, 3, 20])),
                 "unroll": int(rng.choice([1, 2])), "blocks_per_sm": int(rng.choice([0, 0, 2, 7])), "tiles_per_block": int(rng.choice([1, 3])),
-                "pdl": int(rng.choice([0, 1])), "core": int(rng.choice([0, 0, 1])), "second_pass_blocks_per_sm": int(rng.choice([1, 8, 16]))}
+                "pdl": int(rng.choice([0, 1])), "core": int(rng.choice([0, 0, 1])), "second_pass_blocks_per_sm": int(rng.choice([1, 8, 16])),
+                "worklist": int(rng.choice([0, 0, 1, 2, 3])), "hybrid_min_n": int(rng.choice([1 << 26, 1 << 20]))}
         for k, v in opts.items():
             fb.set_option(k, v)
         x = make_input(rng, n)
         hs, hc, hk = fb.host_core(x, opts["core"])
-        mode = int(rng.integers(0, 6))
+        mode = int(rng.integers(0, 7))
         off_in, off_s, off_c = (int(v) for v in rng.integers(0, 4, 3))
         if rng.random() < 0.5:
             off_s = off_c = off_in
@@ -76,6 +77,18 @@ def main():
                 fb.sincos(xv, out_sin=xv, out_cos=bx.new_empty(n))  # in place
                 torch.cuda.synchronize()
                 ok = np.array_equal(bits(so.cpu().numpy()), bits(hs)) and np.array_equal(bits(co.cpu().numpy()), bits(hc)) and np.array_equal(bits(xv.cpu().numpy()), bits(hs))
+        elif mode == 6:  # derived functions: device (misaligned, in place) and host
+            op, fn = [(fb.OP_TAN, fb.tan_array), (fb.OP_COT, fb.cot_array), (fb.OP_SINC, fb.sinc_array)][int(rng.integers(0, 3))]
+            want = fb.host_derived(x, op, opts["core"])
+            bx = torch.zeros(n + 8, dtype=torch.float64, device=dev)
+            bx[off_in:off_in + n] = torch.from_numpy(x).to(dev)
+            xv = bx[off_in:off_in + n]
+            o = fn(xv)
+            fn(xv, out=xv)
+            torch.cuda.synchronize()
+            ok = np.array_equal(bits(o.cpu().numpy()), bits(want)) and np.array_equal(bits(xv.cpu().numpy()), bits(want))
+            if n < 3_000_000:
+                ok = ok and np.array_equal(bits(fn(x)), bits(want))
         elif mode == 3:  # pageable host
             s, c = fb.sincos(x)
             ok = np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
