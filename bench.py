@@ -396,7 +396,7 @@ def run_cuda_arm(args):
             "config": {"workload": desc, "elements_total": n_total, "elements_per_gpu": n_local,
                        "sharding": f"contiguous slices, {world} rank(s), no collective",
                        "core": ["poly", "psi"][fb.get_option("core")], "unroll": fb.get_option("unroll"),
-                       "blocks_per_sm": fb.get_option("blocks_per_sm"),
+                       "blocks_per_sm": fb.get_option("blocks_per_sm"), "worklist": fb.get_option("worklist"),
                        "l2": "inputs+outputs per GPU (%.1f GB) far exceed the 126 MB L2; no flush needed" % (BYTES_PER_ELEM * n_local / 1e9),
                        "implementation": fb.implementation_name()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -404,8 +404,9 @@ def run_cuda_arm(args):
                          "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": BYTES_PER_ELEM * n_local,
                          "step_ms_avg": avg_ms, "step_ms_min": min(step_ms),
-                         "note": "duration = CUDA events around one step on the launching stream (streaming kernel + the "
-                                 "second-pass launch, empty for this workload), rank 0"},
+                         "note": "duration = CUDA events around one step on the launching stream (the fused streaming kernel; "
+                                 "from 2^26 elements per rank on also the counter reset and the second-pass launch, "
+                                 "empty for this workload), rank 0"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
