@@ -153,6 +153,41 @@ __device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& c
     return fabe13_is_plain(ahi);
 }
 
+// ---- the fused kernel's form of the fast path: the quadrant rotation only, NO overrides.  For ordinary data no
+//      lane needs one, and the warp finds that out with the vote it takes anyway -- so the override selects (and the
+//      values they select from) leave the hot path: ~7 of 62 instructions per element.  A warp that does hold a tiny,
+//      special or Payne-Hanek-range lane patches those lanes with patch_lane() before it stores.
+template <int CORE, bool WITH_K, int OUT>
+__device__ __forceinline__ bool plain_lane(uint64_t xb, uint64_t& sb, uint64_t& cb, long long& k) {
+    const double x = __longlong_as_double((long long)xb);
+    double biased;
+    const double kd = fabe13_quadrant_index(x, &biased);
+    const double r = fabe13_cody_waite(x, kd);
+    double sr, cr;
+    fabe13_core<CORE>(r, &sr, &cr);
+    const uint32_t ahi = fabe13_abs_hi(xb);
+    fabe13_rotate(sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
+    if (out_derived(OUT)) sb = fabe13_derived<OUT>(xb, sb, cb);
+    if (WITH_K) k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
+    return fabe13_is_plain(ahi);
+}
+
+// what a lane that is not plain must hold instead: NaN/Inf -> the canonical quiet NaN, |x| <= 2^-27 -> (x, 1) [or the
+// derived function of that pair], Payne-Hanek range -> x itself, parked in the first output the launch writes
+template <int OUT>
+__device__ __forceinline__ void patch_lane(uint64_t xb, uint64_t& sb, uint64_t& cb) {
+    const uint32_t ahi = fabe13_abs_hi(xb);
+    if (fabe13_is_plain(ahi)) return;
+    if (fabe13_is_special(ahi)) {
+        sb = cb = FABE13_QNAN_BITS;
+    } else if (fabe13_is_huge(ahi)) {
+        if (OUT == OUT_COS) cb = xb; else sb = xb;
+    } else {
+        sb = out_derived(OUT) ? fabe13_derived<OUT>(xb, xb, FABE13_ONE_BITS) : xb;
+        cb = FABE13_ONE_BITS;
+    }
+}
+
 // Append this warp's flagged elements (`mine` per lane, indices produced by `emit`) to the block's worklist segment:
 // a warp prefix sum, one atomic for the whole warp, then each lane writes its own run of slots.
 template <typename Emit>
@@ -405,7 +440,16 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+            for (int j = 0; j < VEC; ++j) all_plain &= plain_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
+        }
+    }
+    // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
+    const bool rare = __ballot_sync(0xFFFFFFFFu, !all_plain) != 0;
+    if (rare) {  // tiny, special or Payne-Hanek-range lanes: give them their values / placeholders
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) patch_lane<OUT>(xb[u][j], sb[u][j], cb[u][j]);
         }
     }
 #pragma unroll
@@ -420,8 +464,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
             }
         }
     }
-    // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
-    if (__ballot_sync(0xFFFFFFFFu, !all_plain) != 0) {  // rare: tiny, special or Payne-Hanek-range lanes
+    if (rare) {
         uint32_t n_huge = 0;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
