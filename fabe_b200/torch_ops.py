@@ -3,6 +3,8 @@ roadmap item README.md:227).  Importing this module registers
 
     torch.ops.fabe13.sincos(Tensor x) -> (Tensor sin, Tensor cos)
     torch.ops.fabe13.sin(Tensor x) -> Tensor        torch.ops.fabe13.cos(Tensor x) -> Tensor
+    torch.ops.fabe13.tan(Tensor x) -> Tensor        torch.ops.fabe13.cot(Tensor x) -> Tensor
+    torch.ops.fabe13.sinc(Tensor x) -> Tensor       (unnormalised: sin(x)/x, 1 for |x| < 1e-9, as the reference's)
 
 for float64 tensors: CUDA tensors go to fabe13_sincos_device on the current stream, CPU tensors to fabe13_sincos_host.
 Non-contiguous inputs are made contiguous first.  The operators carry fake (meta) implementations, so they trace
@@ -52,6 +54,23 @@ def register():
     @cos.register_fake
     def _(x):
         return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+    def single(name, fn):
+        op = torch.library.custom_op(f"fabe13::{name}", mutates_args=())(fn)
+        op.register_fake(lambda x: torch.empty_like(x, memory_format=torch.contiguous_format))
+
+    def tan(x: torch.Tensor) -> torch.Tensor:
+        return api.tan_array(_prep(x)).view(x.shape)
+
+    def cot(x: torch.Tensor) -> torch.Tensor:
+        return api.cot_array(_prep(x)).view(x.shape)
+
+    def sinc(x: torch.Tensor) -> torch.Tensor:
+        return api.sinc_array(_prep(x)).view(x.shape)
+
+    single("tan", tan)
+    single("cot", cot)
+    single("sinc", sinc)
 
 
 register()

@@ -43,7 +43,7 @@ def gpu_sincos(fabe13, cuda, x):
 # worklist + second-pass kernel alone (worklist=1), and the hybrid sequence forced at every size (worklist=3).  The
 # heaviest cases run in the default mode only; the tests of the global worklist's own machinery (capacity/overflow
 # rescan, PDL, caller workspace) are skipped where no global worklist exists.
-HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
+HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
          "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
          "test_mixed_host_device_pointers_fail_loudly", "test_native_library_is_the_one_running"}
 GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
@@ -692,6 +692,50 @@ def test_torch_ops_registration(fabe13, cuda, oracle):
         assert torch.equal(torch.ops.fabe13.sin(xt), s) and torch.equal(torch.ops.fabe13.cos(xt), c)
         st, _ = torch.ops.fabe13.sincos(xt.t())  # non-contiguous input
         assert torch.equal(st, s.t())
+        for op, name in ((fabe13.OP_TAN, "tan"), (fabe13.OP_COT, "cot"), (fabe13.OP_SINC, "sinc")):
+            got = getattr(torch.ops.fabe13, name)(xt)
+            assert np.array_equal(bits(got.cpu().numpy().ravel()), bits(fabe13.host_derived(x.ravel(), op)))
+
+
+def test_cuda_graph_capture_and_replay(fabe13, cuda, oracle):
+    """Below hybrid_min_n a call is one kernel launch with no allocation, so it can be captured into a CUDA graph as it
+    is; the hybrid sequence is captured with caller-provided scratch (fabe13_sincos_device_ws).  Replays recompute
+    from whatever the input buffer holds at replay time."""
+    import torch
+
+    lib = fabe13._lib.load()
+    n = 3_000_000
+    x0 = oracle.fill_uniform(n, 71, -1e4, 1e4)
+    x0[::1000] = oracle.fill_loguniform(n // 1000, 72)
+    x1 = oracle.fill_uniform(n, 73, -1e6, 1e6)
+    xt = torch.from_numpy(x0).to(cuda)
+    s = torch.empty_like(xt)
+    c = torch.empty_like(xt)
+    for hybrid in (False, True):
+        fabe13.set_option("worklist", 3 if hybrid else 0)
+        need = lib.fabe13_sincos_workspace_bytes(n)
+        assert (need > 0) == hybrid
+        ws = torch.empty(max(need, 8), dtype=torch.uint8, device=cuda)
+        xt.copy_(torch.from_numpy(x0))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy per-device initialisation)
+            assert lib.fabe13_sincos_device_ws(xt.data_ptr(), s.data_ptr(), c.data_ptr(), n, ws.data_ptr(), need, side.cuda_stream) == 0
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = torch.cuda.current_stream().cuda_stream
+            rc = lib.fabe13_sincos_device_ws(xt.data_ptr(), s.data_ptr(), c.data_ptr(), n, ws.data_ptr(), need, st)
+            assert rc == 0
+        for x in (x0, x1):
+            xt.copy_(torch.from_numpy(x))
+            s.zero_()
+            c.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            hs, hc, _ = fabe13.host_core(x, 0)
+            assert np.array_equal(bits(s.cpu().numpy()), bits(hs)) and np.array_equal(bits(c.cpu().numpy()), bits(hc))
 
 
 def test_host_array_split_over_all_gpus(fabe13, cuda, oracle):
