@@ -29,7 +29,8 @@ using fabe13::DeviceInfo;
 using fabe13::LaunchTuning;
 
 constexpr int kMaxDevices = 64;
-constexpr int kSlots = 8;                                  // pipeline depth of the host path / max staging workers
+constexpr int kSlots = 16;                                 // max staging workers (pageable callers), one slot each
+constexpr int kPipeSlots = 8;                              // pipeline depth for pinned callers (copy engines only)
 constexpr size_t kLaunchMaxElems = (size_t)1 << 30;        // per launch sequence; keeps 32-bit indices and alignment
 constexpr size_t kZeroCopyPageableMax = 32768;             // pageable callers: bounce through one small pinned block
 
@@ -51,7 +52,7 @@ struct Config {
     std::atomic<long long> worklist_shift{3};
     std::atomic<long long> chunk_elems{(long long)1 << 22};
     std::atomic<long long> host_devices{1};
-    std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, hardware threads / 2)
+    std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, 3/4 of the hardware threads)
     std::atomic<long long> zero_copy_max{(long long)1 << 24};
 };
 
@@ -136,13 +137,16 @@ int record(cudaError_t e, const char* where) {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
-    double* d_in = nullptr;   // chunk_cap elements each
+    double* d_in = nullptr;   // cap elements each
     double* d_sin = nullptr;
     double* d_cos = nullptr;
     void* d_ws = nullptr;
     double* h_in = nullptr;   // pinned staging, allocated only when a pageable buffer shows up
     double* h_sin = nullptr;
     double* h_cos = nullptr;
+    size_t cap = 0;        // elements per device buffer
+    size_t ws_bytes = 0;   // bytes of worklist scratch
+    size_t stage_cap = 0;  // elements per pinned staging buffer
 };
 
 struct DeviceState {
@@ -156,9 +160,6 @@ struct DeviceState {
     cudaStream_t small_stream = nullptr;  // small host calls: one kernel reading/writing pinned host memory directly
     double* small_stage = nullptr;        // pinned, 3 * small_cap doubles (in | sin | cos), for pageable callers
     size_t small_cap = 0;
-    size_t chunk_cap = 0;
-    size_t ws_bytes = 0;
-    size_t stage_cap = 0;  // elements per pinned staging buffer (pageable callers only)
     Slot slots[kSlots];
 };
 
@@ -249,62 +250,44 @@ PtrKind classify(const void* p) {
     return PTR_PAGEABLE;
 }
 
-void free_slots(DeviceState& s) {
-    for (Slot& sl : s.slots) {
-        if (sl.d_in) cudaFree(sl.d_in);
-        if (sl.d_sin) cudaFree(sl.d_sin);
-        if (sl.d_cos) cudaFree(sl.d_cos);
-        if (sl.d_ws) cudaFree(sl.d_ws);
-        if (sl.h_in) cudaFreeHost(sl.h_in);
-        if (sl.h_sin) cudaFreeHost(sl.h_sin);
-        if (sl.h_cos) cudaFreeHost(sl.h_cos);
-        sl.d_in = sl.d_sin = sl.d_cos = nullptr;
-        sl.d_ws = nullptr;
-        sl.h_in = sl.h_sin = sl.h_cos = nullptr;
-    }
-    s.chunk_cap = 0;
-    s.stage_cap = 0;
-    s.ws_bytes = 0;
-}
-
-// (re)size the slots of the current device for `chunk` elements; pinned staging only if asked for
-int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning& t) {
-    if (s.chunk_cap < chunk) {
-        free_slots(s);
-        for (Slot& sl : s.slots) {
-            if (!sl.stream) FABE13_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-            if (!sl.done) FABE13_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventBlockingSync | cudaEventDisableTiming));
+// (re)size the first `nslots` slots of the current device for `chunk` elements; pinned staging only if asked for.
+// Capacities are kept per slot: the pinned pipeline uses kPipeSlots large slots, the staging workers up to kSlots
+// small ones.
+int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning& t, int nslots) {
+    const size_t need_ws = fabe13::workspace_bytes(chunk, t);  // depends on the tuning in force
+    for (int i = 0; i < nslots; ++i) {
+        Slot& sl = s.slots[i];
+        if (!sl.stream) FABE13_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.done) FABE13_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventBlockingSync | cudaEventDisableTiming));
+        if (sl.cap < chunk) {
+            if (sl.d_in) FABE13_TRY(cudaFree(sl.d_in));
+            if (sl.d_sin) FABE13_TRY(cudaFree(sl.d_sin));
+            if (sl.d_cos) FABE13_TRY(cudaFree(sl.d_cos));
+            sl.d_in = sl.d_sin = sl.d_cos = nullptr;
+            sl.cap = 0;
             FABE13_TRY(cudaMalloc(&sl.d_in, chunk * sizeof(double)));
             FABE13_TRY(cudaMalloc(&sl.d_sin, chunk * sizeof(double)));
             FABE13_TRY(cudaMalloc(&sl.d_cos, chunk * sizeof(double)));
+            sl.cap = chunk;
         }
-        s.chunk_cap = chunk;
-    }
-    // the worklist scratch depends on the tuning in force (option worklist_shift may change between calls)
-    const size_t need_ws = fabe13::workspace_bytes(s.chunk_cap, t);
-    if (need_ws > 0 && s.ws_bytes < need_ws) {
-        for (Slot& sl : s.slots) {
+        if (need_ws > 0 && sl.ws_bytes < need_ws) {
             if (sl.d_ws) FABE13_TRY(cudaFree(sl.d_ws));
             sl.d_ws = nullptr;
+            sl.ws_bytes = 0;
+            FABE13_TRY(cudaMalloc(&sl.d_ws, need_ws));
+            sl.ws_bytes = need_ws;
         }
-        s.ws_bytes = 0;
-        for (Slot& sl : s.slots) FABE13_TRY(cudaMalloc(&sl.d_ws, need_ws));
-        s.ws_bytes = need_ws;
-    }
-    if (staging && s.stage_cap < chunk) {
-        for (Slot& sl : s.slots) {
+        if (staging && sl.stage_cap < chunk) {
             if (sl.h_in) cudaFreeHost(sl.h_in);
             if (sl.h_sin) cudaFreeHost(sl.h_sin);
             if (sl.h_cos) cudaFreeHost(sl.h_cos);
             sl.h_in = sl.h_sin = sl.h_cos = nullptr;
-        }
-        s.stage_cap = 0;
-        for (Slot& sl : s.slots) {
+            sl.stage_cap = 0;
             FABE13_TRY(cudaHostAlloc(&sl.h_in, chunk * sizeof(double), cudaHostAllocDefault));
             FABE13_TRY(cudaHostAlloc(&sl.h_sin, chunk * sizeof(double), cudaHostAllocDefault));
             FABE13_TRY(cudaHostAlloc(&sl.h_cos, chunk * sizeof(double), cudaHostAllocDefault));
+            sl.stage_cap = chunk;
         }
-        s.stage_cap = chunk;
     }
     return 0;
 }
@@ -399,24 +382,24 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     }
     size_t chunk = pick_chunk(n);
     if (!pinned && chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;  // staged: 8 MB pieces, one per worker in flight
-    if (int rc = ensure_slots(*ds, chunk, !pinned, t)) return rc;
     const size_t nchunks = (n + chunk - 1) / chunk;
 
     if (pinned) {
+        if (int rc = ensure_slots(*ds, chunk, false, t, kPipeSlots)) return rc;
         // copy engines read and write the caller's pinned memory directly; one host thread feeds all slots
         for (size_t i = 0; i < nchunks; ++i) {
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
-            if (int rc = enqueue_chunk(*ds, ds->slots[i % kSlots], in + off, sin_out ? sin_out + off : nullptr,
+            if (int rc = enqueue_chunk(*ds, ds->slots[i % kPipeSlots], in + off, sin_out ? sin_out + off : nullptr,
                                        cos_out ? cos_out + off : nullptr, m, t, core, op))
                 return rc;
         }
         if (n >= ((size_t)1 << 22)) {
             // large transfers: sleep on blocking events rather than spin (the wait is milliseconds long)
-            for (Slot& sl : ds->slots) FABE13_TRY(cudaEventRecord(sl.done, sl.stream));
-            for (Slot& sl : ds->slots) FABE13_TRY(cudaEventSynchronize(sl.done));
+            for (int i = 0; i < kPipeSlots; ++i) FABE13_TRY(cudaEventRecord(ds->slots[i].done, ds->slots[i].stream));
+            for (int i = 0; i < kPipeSlots; ++i) FABE13_TRY(cudaEventSynchronize(ds->slots[i].done));
         } else {
-            for (Slot& sl : ds->slots) FABE13_TRY(cudaStreamSynchronize(sl.stream));
+            for (int i = 0; i < kPipeSlots; ++i) FABE13_TRY(cudaStreamSynchronize(ds->slots[i].stream));
         }
         return 0;
     }
@@ -425,10 +408,14 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     // staging, runs it, waits, and copies the results out.  Workers overlap each other's stages.
     int workers = (int)g_cfg.stage_threads.load();
     if (workers <= 0) {
+        // the staging copies are what bounds this path (measured: throughput still grows linearly from 8 to 12
+        // threads on a 16-thread host), so take most of the machine; the caller's own thread is worker 0
         const unsigned hw = std::thread::hardware_concurrency();
-        workers = (int)(hw / 2 > (unsigned)kSlots ? (unsigned)kSlots : (hw / 2 ? hw / 2 : 1));
+        const unsigned want = hw - hw / 4;
+        workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
     }
     if ((size_t)workers > nchunks) workers = (int)nchunks;
+    if (int rc = ensure_slots(*ds, chunk, true, t, workers)) return rc;
     std::atomic<int> rc_all{0};
     auto work = [&](int w) {
         if (cudaSetDevice(dev) != cudaSuccess) {
