@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     get_option,
     host_core,
     host_derived,
+    host_sincosf,
     implementation_name,
     set_option,
     shard_bounds,
@@ -30,6 +31,7 @@ from .api import (  # noqa: F401
     sinc_array,
     sincos,
     sincos_k,
+    sincosf,
     sincos_legacy,
     tan,
     tan_array,

@@ -44,6 +44,8 @@ def signatures():
         "fabe13_tan_host": (c.c_int, [_vp, _vp, c.c_size_t]),
         "fabe13_cot_host": (c.c_int, [_vp, _vp, c.c_size_t]),
         "fabe13_sinc_host": (c.c_int, [_vp, _vp, c.c_size_t]),
+        "fabe13_sincosf_device": (c.c_int, [_vp, _vp, _vp, c.c_size_t, _vp]),
+        "fabe13_sincosf_host": (c.c_int, [_vp, _vp, _vp, c.c_size_t]),
         "fabe13_sincos_workspace_bytes": (c.c_size_t, [c.c_size_t]),
         "fabe13_sincos_device_ws": (c.c_int, [_vp, _vp, _vp, c.c_size_t, _vp, c.c_size_t, _vp]),
         "fabe13_sincos_multi": (c.c_int, [c.c_int, _vp, _vp, _vp, _vp, _vp]),
@@ -60,6 +62,7 @@ def signatures():
         "fabe13_cuda_last_error_string": (c.c_char_p, []),
         "fabe13_cuda_clear_error": (None, []),
         "fabe13_debug_host_core": (None, [_vp, _vp, _vp, _vp, c.c_size_t, c.c_int]),
+        "fabe13_debug_host_sincosf": (None, [_vp, _vp, _vp, c.c_size_t, c.c_int]),
         "fabe13_debug_host_derived": (None, [_vp, _vp, c.c_size_t, c.c_int, c.c_int]),
         "fabe13_debug_fill_uniform_device": (c.c_int, [_vp, c.c_size_t, c.c_uint64, c.c_uint64, c.c_double, c.c_double, _vp]),
         "fabe13_debug_fill_loguniform_device": (c.c_int, [_vp, c.c_size_t, c.c_uint64, c.c_uint64, _vp]),

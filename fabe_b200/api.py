@@ -115,6 +115,42 @@ def sinc_array(x, out=None):
 OP_TAN, OP_COT, OP_SINC = 3, 4, 5
 
 
+def sincosf(x, out_sin=None, out_cos=None):
+    """(sin(x), cos(x)) for a float32 array: torch CUDA tensor -> fabe13_sincosf_device on the current stream;
+    numpy array / torch CPU tensor -> fabe13_sincosf_host (synchronous)."""
+    lib = _lib.load()
+    if _is_torch(x):
+        import torch
+
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            raise TypeError("x must be a contiguous float32 tensor")
+        s = torch.empty_like(x) if out_sin is None else out_sin
+        c = torch.empty_like(x) if out_cos is None else out_cos
+        if x.is_cuda:
+            with torch.cuda.device(x.device):
+                rc = lib.fabe13_sincosf_device(x.data_ptr(), s.data_ptr(), c.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = lib.fabe13_sincosf_host(x.data_ptr(), s.data_ptr(), c.data_ptr(), x.numel())
+        _lib.check(rc, "fabe13_sincosf")
+        return s, c
+    if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+        raise TypeError("x must be a C-contiguous float32 array")
+    s = np.empty_like(x) if out_sin is None else out_sin
+    c = np.empty_like(x) if out_cos is None else out_cos
+    _lib.check(lib.fabe13_sincosf_host(x.ctypes.data, s.ctypes.data, c.ctypes.data, x.size), "fabe13_sincosf_host")
+    return s, c
+
+
+def host_sincosf(x, core=CORE_POLY):
+    """Test hook: the FP32 entry's arithmetic on the host (widen, shared FP64 core, round once)."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    lib.fabe13_debug_host_sincosf(x.ctypes.data, s.ctypes.data, c.ctypes.data, x.size, core)
+    return s, c
+
+
 def sincos_k(x):
     """(sin, cos, k) for a torch CUDA float64 tensor; k is the reference's quadrant index (test hook)."""
     import torch

@@ -40,6 +40,10 @@ cudaError_t launch_sincos(const double* d_in, double* d_sin, double* d_cos, long
                           const LaunchTuning& tuning, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                           int* launches);
 
+// FP32 arrays (12 B/element): the same per-element algorithm in FP64 arithmetic, results rounded once to float.
+cudaError_t launch_sincosf(const float* d_in, float* d_sin, float* d_cos, size_t n, int core, const DeviceInfo& dev,
+                           cudaStream_t stream, int* launches);
+
 // Bench/test hooks: synthetic inputs generated on the device (bit-identical to oracle/fabe13_oracle.c's fills).
 cudaError_t fill_uniform(double* d_out, size_t n, uint64_t seed, uint64_t first, double lo, double hi,
                          const DeviceInfo& dev, cudaStream_t stream);

@@ -668,6 +668,81 @@ __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* i
     }
 }
 
+// ---- FP32 arrays: sincosf -----------------------------------------------------------------------------------------
+// The reference has no FP32 path (roadmap only, README.md:225); this is the array path's own algorithm applied to
+// float data: each element is widened to FP64 (exact), goes through the same k / Cody-Waite / core / fix-up code as
+// the FP64 kernels (Payne-Hanek inline for the rare |x| >= 2^45), and both results are rounded once to FP32.  The
+// results are therefore the correctly rounded float sin/cos except where the FP64 value (error <= 1.1e-16) falls
+// within that distance of a rounding boundary.  12 bytes of HBM traffic per element: one 256-bit load of eight floats
+// per thread, two 256-bit stores; tiles in address order, one per block.
+#ifndef FABE13_SINCOSF_MIN_BLOCKS
+#define FABE13_SINCOSF_MIN_BLOCKS 6
+#endif
+struct SincosfArgs {
+    const float* in;
+    float* sin_out;
+    float* cos_out;
+    uint32_t n;      // elements in this launch
+    uint32_t head;   // scalar elements before the 32-byte aligned body
+    uint32_t nvec;   // 8-float vectors in the body (0 when the three arrays are not congruent modulo 32 bytes)
+};
+
+struct BitsPair {
+    uint64_t s, c;
+};
+// the every-range routine, out of line: eight inlined copies per thread would set the kernel's register count
+template <int CORE>
+__device__ __noinline__ BitsPair sincos_any_range(uint64_t xb) {
+    BitsPair r;
+    int64_t k;
+    fabe13_sincos_one<CORE>(xb, c_ph_stream, &r.s, &r.c, &k);
+    return r;
+}
+
+template <int CORE>
+__device__ __forceinline__ void sincosf_one(float xf, float& sf, float& cf) {
+    const uint64_t xb = (uint64_t)__double_as_longlong((double)xf);
+    uint64_t sb, cb;
+    long long k;
+    if (!plain_lane<CORE, false, OUT_BOTH>(xb, sb, cb, k)) {  // tiny, NaN/Inf, Payne-Hanek range (rare)
+        const BitsPair r = sincos_any_range<CORE>(xb);
+        sb = r.s;
+        cb = r.c;
+    }
+    sf = __double2float_rn(__longlong_as_double((long long)sb));
+    cf = __double2float_rn(__longlong_as_double((long long)cb));
+}
+
+template <int CORE>
+__global__ void __launch_bounds__(kThreads, FABE13_SINCOSF_MIN_BLOCKS) sincosf_kernel(const SincosfArgs a) {
+    const uint32_t v = blockIdx.x * kThreads + threadIdx.x;
+    if (v < a.nvec) {
+        uint64_t w[4];
+        load_stream<4>(reinterpret_cast<const double*>(a.in + a.head) + (size_t)v * 4, w);
+        uint64_t so[4], co[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s0, c0, s1, c1;
+            sincosf_one<CORE>(__uint_as_float((uint32_t)w[j]), s0, c0);
+            sincosf_one<CORE>(__uint_as_float((uint32_t)(w[j] >> 32)), s1, c1);
+            so[j] = (uint64_t)__float_as_uint(s0) | ((uint64_t)__float_as_uint(s1) << 32);
+            co[j] = (uint64_t)__float_as_uint(c0) | ((uint64_t)__float_as_uint(c1) << 32);
+        }
+        store_stream<4>(a.sin_out + a.head + (size_t)v * 8, so);
+        store_stream<4>(a.cos_out + a.head + (size_t)v * 8, co);
+    }
+    // what the vectors do not cover: the head, the tail, or everything when the arrays are mutually misaligned
+    const uint32_t body_end = a.head + a.nvec * 8;
+    const uint32_t n_edge = a.head + (a.n - body_end);
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_edge; i += gridDim.x * kThreads) {
+        const uint32_t idx = i < a.head ? i : body_end + (i - a.head);
+        float sf, cf;
+        sincosf_one<CORE>(a.in[idx], sf, cf);
+        a.sin_out[idx] = sf;
+        a.cos_out[idx] = cf;
+    }
+}
+
 // ---- bench/test hooks: the synthetic inputs of SURVEY.md section 8d, generated in place on the device.
 //      Counter-based (splitmix64 of seed + global index), so any slice of any sharding reproduces the same array
 //      and the host generator in oracle/fabe13_oracle.c yields identical bits.
@@ -878,6 +953,38 @@ cudaError_t fill_loguniform(double* d_out, size_t n, uint64_t seed, uint64_t fir
                             cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     fill_loguniform_kernel<<<dev.sm_count * 8, kThreads, 0, stream>>>(d_out, n, seed, first);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sincosf(const float* d_in, float* d_sin, float* d_cos, size_t n, int core, const DeviceInfo& dev,
+                           cudaStream_t stream, int* launches) {
+    if (n == 0) return cudaSuccess;
+    if (n > ((size_t)1 << 31) || !d_in || !d_sin || !d_cos) return cudaErrorInvalidValue;
+    const uintptr_t pi = (uintptr_t)d_in, ps = (uintptr_t)d_sin, pc = (uintptr_t)d_cos;
+    SincosfArgs a;
+    a.in = d_in;
+    a.sin_out = d_sin;
+    a.cos_out = d_cos;
+    a.n = (uint32_t)n;
+    a.head = 0;
+    a.nvec = 0;
+    if ((pi & 31) == (ps & 31) && (pi & 31) == (pc & 31) && (pi & 3) == 0) {  // one 32-byte phase for all three arrays
+        size_t head = ((32 - (pi & 31)) & 31) / 4;
+        if (head > n) head = n;
+        a.head = (uint32_t)head;
+        a.nvec = (uint32_t)((n - head) / 8);
+    }
+    const size_t edge = n - (size_t)a.nvec * 8;
+    long long grid = ((long long)a.nvec + kThreads - 1) / kThreads;
+    const long long edge_blocks = (long long)((edge + kThreads - 1) / kThreads);
+    const long long cap = (long long)dev.sm_count * 64;
+    if (grid < (edge_blocks < cap ? edge_blocks : cap)) grid = edge_blocks < cap ? edge_blocks : cap;
+    if (grid < 1) grid = 1;
+    if (core == FABE13_CORE_PSI)
+        sincosf_kernel<FABE13_CORE_PSI><<<(unsigned)grid, kThreads, 0, stream>>>(a);
+    else
+        sincosf_kernel<FABE13_CORE_POLY><<<(unsigned)grid, kThreads, 0, stream>>>(a);
+    *launches += 1;
     return cudaGetLastError();
 }
 

@@ -502,6 +502,79 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FP32 arrays.  Device pointers: one launch.  Pinned (or registered) host arrays: the kernel reads and writes them in
+// place over PCIe (12 B/element either way).  Pageable host arrays: 4M-element pieces through a pinned bounce buffer.
+// ---------------------------------------------------------------------------------------------------------------
+int run_device_f32(const float* d_in, float* d_sin, float* d_cos, size_t n, cudaStream_t stream) {
+    if (n == 0) return 0;
+    DeviceState* ds;
+    if (int rc = current_device_state(&ds)) return rc;
+    const int core = (int)g_cfg.core.load();
+    for (size_t off = 0; off < n; off += kLaunchMaxElems) {
+        const size_t m = (n - off < kLaunchMaxElems) ? n - off : kLaunchMaxElems;
+        int launches = 0;
+        cudaError_t e = fabe13::launch_sincosf(d_in + off, d_sin + off, d_cos + off, m, core, ds->info, stream, &launches);
+        g_launches.fetch_add((unsigned long long)launches);
+        if (e != cudaSuccess) return record(e, "launch_sincosf");
+    }
+    return 0;
+}
+
+int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
+    if (n == 0) return 0;
+    load_env();
+    if (!in || !sin_out || !cos_out) return record(cudaErrorInvalidValue, "fabe13_sincosf_host: null array");
+    const PtrKind ki = classify(in), ks = classify(sin_out), kc = classify(cos_out);
+    if (ki == PTR_DEVICE || ks == PTR_DEVICE || kc == PTR_DEVICE) {
+        if (!(ki == PTR_DEVICE && ks == PTR_DEVICE && kc == PTR_DEVICE))
+            return record(cudaErrorInvalidValue, "fabe13_sincosf_host: mixed host and device pointers");
+        if (int rc = run_device_f32(in, sin_out, cos_out, n, nullptr)) return rc;
+        FABE13_TRY(cudaStreamSynchronize(nullptr));
+        return 0;
+    }
+    DeviceState* ds;
+    if (int rc = current_device_state(&ds)) return rc;
+    std::lock_guard<std::mutex> lk(ds->pipe_mu);
+    if (!ds->small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&ds->small_stream, cudaStreamNonBlocking));
+    if (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED) {
+        void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
+        if (cudaHostGetDevicePointer(&d_in, (void*)in, 0) == cudaSuccess && cudaHostGetDevicePointer(&d_s, sin_out, 0) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d_c, cos_out, 0) == cudaSuccess) {
+            if (int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, n, ds->small_stream)) return rc;
+            FABE13_TRY(cudaStreamSynchronize(ds->small_stream));
+            return 0;
+        }
+        (void)cudaGetLastError();  // registered without a device mapping: stage it like pageable memory
+    }
+    const size_t piece = (size_t)1 << 22;  // floats per piece: 3 x 16 MB of pinned staging
+    const size_t need_doubles = (3 * piece * sizeof(float) + sizeof(double) - 1) / sizeof(double);
+    if (ds->small_cap * 3 < need_doubles) {
+        if (ds->small_stage) cudaFreeHost(ds->small_stage);
+        ds->small_stage = nullptr;
+        ds->small_cap = 0;
+        const size_t cap = (need_doubles + 2) / 3;
+        FABE13_TRY(cudaHostAlloc(&ds->small_stage, 3 * cap * sizeof(double), cudaHostAllocDefault));
+        ds->small_cap = cap;
+    }
+    float* h_in = reinterpret_cast<float*>(ds->small_stage);
+    float* h_s = h_in + piece;
+    float* h_c = h_s + piece;
+    void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
+    FABE13_TRY(cudaHostGetDevicePointer(&d_in, h_in, 0));
+    FABE13_TRY(cudaHostGetDevicePointer(&d_s, h_s, 0));
+    FABE13_TRY(cudaHostGetDevicePointer(&d_c, h_c, 0));
+    for (size_t off = 0; off < n; off += piece) {
+        const size_t m = n - off < piece ? n - off : piece;
+        memcpy(h_in, in + off, m * sizeof(float));
+        if (int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, m, ds->small_stream)) return rc;
+        FABE13_TRY(cudaStreamSynchronize(ds->small_stream));
+        memcpy(sin_out + off, h_s, m * sizeof(float));
+        memcpy(cos_out + off, h_c, m * sizeof(float));
+    }
+    return 0;
+}
+
 int cfg_core() {
     load_env();
     return (int)g_cfg.core.load();
@@ -623,6 +696,13 @@ int fabe13_sinc_device(const double* d_in, double* d_out, size_t n, void* cuda_s
 int fabe13_tan_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_TAN, "fabe13_tan_host: null output"); }
 int fabe13_cot_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_COT, "fabe13_cot_host: null output"); }
 int fabe13_sinc_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_SINC, "fabe13_sinc_host: null output"); }
+
+// FP32 arrays (the reference's roadmap item README.md:225; no reference implementation exists)
+int fabe13_sincosf_device(const float* d_in, float* d_sin, float* d_cos, size_t n, void* cuda_stream) {
+    if (n && (!d_in || !d_sin || !d_cos)) return record(cudaErrorInvalidValue, "fabe13_sincosf_device: null array");
+    return run_device_f32(d_in, d_sin, d_cos, n, (cudaStream_t)cuda_stream);
+}
+int fabe13_sincosf_host(const float* in, float* sin_out, float* cos_out, size_t n) { return run_host_f32(in, sin_out, cos_out, n); }
 
 int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
                            void* cuda_stream) {
@@ -750,6 +830,15 @@ void fabe13_cuda_clear_error(void) { g_last_error.store(0); }
 
 void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core) {
     for (size_t i = 0; i < n; ++i) host_one(in[i], core, &sin_out[i], &cos_out[i], k_out ? &k_out[i] : nullptr);
+}
+
+void fabe13_debug_host_sincosf(const float* in, float* sin_out, float* cos_out, size_t n, int core) {
+    for (size_t i = 0; i < n; ++i) {
+        double s, c;
+        host_one((double)in[i], core, &s, &c, nullptr);
+        sin_out[i] = (float)s;  // round to nearest even, as cvt.rn.f32.f64 on the device
+        cos_out[i] = (float)c;
+    }
 }
 
 void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, int core) {

@@ -52,6 +52,16 @@ int fabe13_tan_host(const double* in, double* out, size_t n);
 int fabe13_cot_host(const double* in, double* out, size_t n);
 int fabe13_sinc_host(const double* in, double* out, size_t n);
 
+/* FP32 arrays (the reference lists an FP32 path on its roadmap only, README.md:225; there is no reference
+ * implementation to be in parity with).  Each element is widened to FP64, goes through the same algorithm as
+ * fabe13_sincos -- every range, Payne-Hanek included -- and both results are rounded once to float: the correctly
+ * rounded float sine and cosine except within 1.1e-16 (absolute) of a rounding boundary.  NaN/Inf -> 0x7FC00000 in both
+ * outputs; |x| <= 2^-27 -> (x, 1.0f).  12 bytes of traffic per element.  Arrays must be 4-byte aligned; 256-bit accesses
+ * are used when the three arrays share one phase modulo 32 bytes.  The host entry takes device, pinned/registered
+ * (processed in place over PCIe) or pageable memory (staged in 4M-element pieces). */
+int fabe13_sincosf_device(const float* d_in, float* d_sin, float* d_cos, size_t n, void* cuda_stream);
+int fabe13_sincosf_host(const float* in, float* sin_out, float* cos_out, size_t n);
+
 /* Same as fabe13_sincos_device with caller-provided scratch of at least fabe13_sincos_workspace_bytes(n) bytes
  * (no allocation on the call path; usable inside CUDA graph capture on any toolkit).  The size may be 0 (small n,
  * or option "worklist" = 2); a NULL workspace is accepted exactly then. */
@@ -107,6 +117,7 @@ void fabe13_cuda_clear_error(void);
 /* Test hook, never on a product path: evaluates the shared per-element core on the HOST for n elements
  * (same code the kernels compile for the device).  Lets CPU-only CI check the algorithm without a GPU. */
 void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core);
+void fabe13_debug_host_sincosf(const float* in, float* sin_out, float* cos_out, size_t n, int core);
 /* Same for the derived functions: op = 3 (tan), 4 (cot), 5 (sinc). */
 void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, int core);
 

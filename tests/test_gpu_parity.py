@@ -43,7 +43,8 @@ def gpu_sincos(fabe13, cuda, x):
 # worklist + second-pass kernel alone (worklist=1), and the hybrid sequence forced at every size (worklist=3).  The
 # heaviest cases run in the default mode only; the tests of the global worklist's own machinery (capacity/overflow
 # rescan, PDL, caller workspace) are skipped where no global worklist exists.
-HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
+HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay",
+         "test_sincosf_device_matches_host_bit_for_bit", "test_sincosf_host_entries", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
          "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
          "test_mixed_host_device_pointers_fail_loudly", "test_native_library_is_the_one_running"}
 GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
@@ -695,6 +696,67 @@ def test_torch_ops_registration(fabe13, cuda, oracle):
         for op, name in ((fabe13.OP_TAN, "tan"), (fabe13.OP_COT, "cot"), (fabe13.OP_SINC, "sinc")):
             got = getattr(torch.ops.fabe13, name)(xt)
             assert np.array_equal(bits(got.cpu().numpy().ravel()), bits(fabe13.host_derived(x.ravel(), op)))
+
+
+@pytest.mark.parametrize("core", [0, 1])
+def test_sincosf_device_matches_host_bit_for_bit(fabe13, cuda, core):
+    """FP32 arrays: the device kernel and the host instantiation of the same arithmetic agree in every bit -- uniform
+    data, every float32 bit pattern class (subnormals, NaN payloads, huge), every mutual alignment, in place."""
+    import torch
+
+    fabe13.set_option("core", core)
+    rng = np.random.default_rng(9)
+    n = 3_000_017
+    x = rng.uniform(-1e4, 1e4, n).astype(np.float32)
+    x[100_000:400_000] = rng.integers(0, 1 << 32, 300_000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    x[::1001] = np.float32(3.0e38)
+    hs, hc = fabe13.host_sincosf(x, core)
+    xt = torch.from_numpy(x).to(cuda)
+    s, c = fabe13.sincosf(xt)
+    torch.cuda.synchronize()
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), hs.view(np.uint32))
+    assert np.array_equal(c.cpu().numpy().view(np.uint32), hc.view(np.uint32))
+    for off_in, off_s, off_c in ((1, 1, 1), (3, 3, 3), (0, 1, 0), (5, 5, 2), (8, 8, 8)):   # vector path only when congruent
+        m = 200_003
+        bs = torch.zeros(m + 16, dtype=torch.float32, device=cuda)
+        bc = torch.zeros(m + 16, dtype=torch.float32, device=cuda)
+        fabe13.sincosf(xt[off_in:off_in + m], out_sin=bs[off_s:off_s + m], out_cos=bc[off_c:off_c + m])
+        torch.cuda.synchronize()
+        assert np.array_equal(bs[off_s:off_s + m].cpu().numpy().view(np.uint32), hs[off_in:off_in + m].view(np.uint32))
+        assert np.array_equal(bc[off_c:off_c + m].cpu().numpy().view(np.uint32), hc[off_in:off_in + m].view(np.uint32))
+        assert float(bs[:off_s].abs().sum()) == 0 and float(bs[off_s + m:].abs().sum()) == 0   # nothing written outside
+    y = xt.clone()
+    c2 = torch.empty_like(y)
+    fabe13.sincosf(y, out_sin=y, out_cos=c2)                                                    # in place
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy().view(np.uint32), hs.view(np.uint32))
+    for k in (1, 7, 9, 100):                                                                    # tiny arrays
+        s, c = fabe13.sincosf(xt[:k].clone())
+        torch.cuda.synchronize()
+        assert np.array_equal(s.cpu().numpy().view(np.uint32), hs[:k].view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [5, 100_000, 9_000_001])
+def test_sincosf_host_entries(fabe13, cuda, n):
+    """Pageable numpy arrays (staged pieces), page-locked arrays (processed in place over PCIe), legacy-style sync."""
+    lib = fabe13._lib.load()
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1e5, 1e5, n).astype(np.float32)
+    hs, hc = fabe13.host_sincosf(x)
+    s, c = fabe13.sincosf(x)
+    assert np.array_equal(s.view(np.uint32), hs.view(np.uint32)) and np.array_equal(c.view(np.uint32), hc.view(np.uint32))
+    s2 = np.zeros_like(x)
+    c2 = np.zeros_like(x)
+    for a in (x, s2, c2):
+        assert lib.fabe13_cuda_host_register(a.ctypes.data, max(a.nbytes, 4096)) == 0 or n < 1024
+    lib.fabe13_cuda_clear_error()
+    try:
+        fabe13.sincosf(x, out_sin=s2, out_cos=c2)
+    finally:
+        for a in (x, s2, c2):
+            lib.fabe13_cuda_host_unregister(a.ctypes.data)
+        lib.fabe13_cuda_clear_error()
+    assert np.array_equal(s2.view(np.uint32), hs.view(np.uint32)) and np.array_equal(c2.view(np.uint32), hc.view(np.uint32))
 
 
 def test_cuda_graph_capture_and_replay(fabe13, cuda, oracle):

@@ -169,3 +169,31 @@ def test_scalar_derived_api_is_the_array_code(fabe13, oracle):
         want = fabe13.host_derived(x, op)
         got = np.array([fn(v) for v in x])
         assert np.array_equal(bits(got), bits(want))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FP32 arrays (last item): widen, the FP64 core, round once
+# ---------------------------------------------------------------------------------------------------------------
+def test_sincosf_is_the_correctly_rounded_float_result(fabe13):
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-1e4, 1e4, 400_000), rng.uniform(-4, 4, 200_000),
+                        np.ldexp(rng.uniform(-2, 2, 200_000), rng.integers(-140, 128, 200_000))]).astype(np.float32)
+    s, c = fabe13.host_sincosf(x)
+    xd = x.astype(np.float64)
+    ws, wc = np.sin(xd).astype(np.float32), np.cos(xd).astype(np.float32)   # glibc double (<= 1 ulp of double), rounded once
+    # identical except where the two double values straddle a float rounding boundary: at most a handful, 1 ulp apart
+    for got, want in ((s, ws), (c, wc)):
+        diff = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+        assert diff.max() <= 1 and np.count_nonzero(diff) <= 3
+    assert np.all(np.abs(s.astype(np.float64) - np.sin(xd)) <= 0.5000001 * np.spacing(np.abs(s)).astype(np.float64) + 1e-45)
+
+
+def test_sincosf_specials(fabe13):
+    x = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 2.0**-27, 3.0e38, -3.0e38], dtype=np.float32)
+    x[4:5].view(np.uint32)[:] = 0xFFC01234                                     # negative NaN with a payload
+    s, c = fabe13.host_sincosf(x)
+    assert np.array_equal(s[:2].view(np.uint32), x[:2].view(np.uint32)) and np.all(c[:2] == 1.0)
+    assert np.all(s[2:5].view(np.uint32) == 0x7FC00000) and np.all(c[2:5].view(np.uint32) == 0x7FC00000)
+    assert s[5] == x[5] and c[5] == 1.0 and s[6] == x[6] and c[6] == 1.0         # tiny: (x, 1) bit for bit
+    big = x[7:].astype(np.float64)
+    assert np.array_equal(s[7:], np.sin(big).astype(np.float32)) and np.array_equal(c[7:], np.cos(big).astype(np.float32))
