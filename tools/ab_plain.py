@@ -40,7 +40,8 @@ def run(lib, x, s, c, n, steps):
 
 
 def main():
-    libs = [("default", LIBPATH)] + [tuple(a.split("=", 1)) for a in sys.argv[1:]]
+    c4 = "--c4" in sys.argv
+    libs = [("default", LIBPATH)] + [tuple(a.split("=", 1)) for a in sys.argv[1:] if not a.startswith("--")]
     loaded = []
     for name, spec in libs:  # spec = path[:option=value[:option=value ...]]
         path, *opts = spec.split(":")
@@ -57,6 +58,21 @@ def main():
     c = torch.empty_like(x)
     libs[0][1].fabe13_debug_fill_uniform_device(x.data_ptr(), n, 0xFABE1303, 0, -1e4, 1e4, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+    if c4:  # BASELINE config 4: N = 1e8, |x| log-uniform to 2^1024 (dense Payne-Hanek), plus two mixes
+        import fabe_b200 as fb
+
+        m = 100_000_000
+        for label, step in (("c4 dense", 1), ("every 2nd huge", 2), ("5% huge", 20)):
+            fb.fill_uniform_device(x[:m], 0xFABE1302, -1e4, 1e4)
+            h = torch.empty((m + step - 1) // step, dtype=torch.float64, device=dev)
+            fb.fill_loguniform_device(h, 0xFABE1304)
+            x[:m][::step] = h
+            torch.cuda.synchronize()
+            for rep in range(3):
+                for name, lib in libs:
+                    avg, best = run(lib, x, s, c, m, 20)
+                    print(f"rep {rep} {name:24s} {label:16s} 1e8 (20)  avg {avg:7.2f} best {best:7.2f} Gelem/s", flush=True)
+        return
     for rep in range(3):
         for name, lib in libs:
             avg, best = run(lib, x, s, c, n, 20)
