@@ -670,10 +670,10 @@ __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* i
 
 // ---- FP32 arrays: sincosf -----------------------------------------------------------------------------------------
 // The reference has no FP32 path (roadmap only, README.md:225); this is the array path's own algorithm applied to
-// float data: each element is widened to FP64 (exact), goes through the same k / Cody-Waite / core / fix-up code as
-// the FP64 kernels (Payne-Hanek inline for the rare |x| >= 2^45), and both results are rounded once to FP32.  The
-// results are therefore the correctly rounded float sin/cos except where the FP64 value (error <= 1.1e-16) falls
-// within that distance of a rounding boundary.  12 bytes of HBM traffic per element: one 256-bit load of eight floats
+// float data: each element is widened to FP64 (exact), reduced and evaluated in FP64 -- plain arguments by a shorter
+// route than the FP64 entries need (fabe13_core.h section 6: 16 FP64 instructions, good to 3e-12), everything else by
+// the every-range routine -- and both results are rounded once to FP32: within 0.5001 ulp of the true values, the
+// correctly rounded float in all but ~1e-4 of the cases.  12 bytes of HBM traffic per element: one 256-bit load of eight floats
 // per thread, two 256-bit stores; tiles in address order, one per block.
 #ifndef FABE13_SINCOSF_MIN_BLOCKS
 #define FABE13_SINCOSF_MIN_BLOCKS 6
@@ -699,18 +699,19 @@ __device__ __noinline__ BitsPair sincos_any_range(uint64_t xb) {
     return r;
 }
 
+// one float: the short FP64 route for plain arguments (fabe13_sincosf_one in fabe13_core.h, restated here so that
+// the rare branch is a call), results rounded once
 template <int CORE>
 __device__ __forceinline__ void sincosf_one(float xf, float& sf, float& cf) {
-    const uint64_t xb = (uint64_t)__double_as_longlong((double)xf);
-    uint64_t sb, cb;
-    long long k;
-    if (!plain_lane<CORE, false, OUT_BOTH>(xb, sb, cb, k)) {  // tiny, NaN/Inf, Payne-Hanek range (rare)
+    const double x = (double)xf;
+    const uint64_t xb = (uint64_t)__double_as_longlong(x);
+    if (CORE == FABE13_CORE_POLY && fabe13_is_plain(fabe13_abs_hi(xb))) {
+        fabe13_sincosf_one<CORE>(xf, c_ph_stream, &sf, &cf);  // the compiler keeps only the plain branch here
+    } else {  // tiny, NaN/Inf, Payne-Hanek range (rare), or the Psi core
         const BitsPair r = sincos_any_range<CORE>(xb);
-        sb = r.s;
-        cb = r.c;
+        sf = __double2float_rn(__longlong_as_double((long long)r.s));
+        cf = __double2float_rn(__longlong_as_double((long long)r.c));
     }
-    sf = __double2float_rn(__longlong_as_double((long long)sb));
-    cf = __double2float_rn(__longlong_as_double((long long)cb));
 }
 
 template <int CORE>

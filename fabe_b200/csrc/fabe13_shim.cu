@@ -834,10 +834,10 @@ void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, 
 
 void fabe13_debug_host_sincosf(const float* in, float* sin_out, float* cos_out, size_t n, int core) {
     for (size_t i = 0; i < n; ++i) {
-        double s, c;
-        host_one((double)in[i], core, &s, &c, nullptr);
-        sin_out[i] = (float)s;  // round to nearest even, as cvt.rn.f32.f64 on the device
-        cos_out[i] = (float)c;
+        if (core == FABE13_CORE_PSI)
+            fabe13_sincosf_one<FABE13_CORE_PSI>(in[i], h_ph_stream, &sin_out[i], &cos_out[i]);
+        else
+            fabe13_sincosf_one<FABE13_CORE_POLY>(in[i], h_ph_stream, &sin_out[i], &cos_out[i]);
     }
 }
 

@@ -53,12 +53,13 @@ int fabe13_cot_host(const double* in, double* out, size_t n);
 int fabe13_sinc_host(const double* in, double* out, size_t n);
 
 /* FP32 arrays (the reference lists an FP32 path on its roadmap only, README.md:225; there is no reference
- * implementation to be in parity with).  Each element is widened to FP64, goes through the same algorithm as
- * fabe13_sincos -- every range, Payne-Hanek included -- and both results are rounded once to float: the correctly
- * rounded float sine and cosine except within 1.1e-16 (absolute) of a rounding boundary.  NaN/Inf -> 0x7FC00000 in both
- * outputs; |x| <= 2^-27 -> (x, 1.0f).  12 bytes of traffic per element.  Arrays must be 4-byte aligned; 256-bit accesses
- * are used when the three arrays share one phase modulo 32 bytes.  The host entry takes device, pinned/registered
- * (processed in place over PCIe) or pageable memory (staged in 4M-element pieces). */
+ * implementation to be in parity with).  Each element is widened to FP64, reduced and evaluated in FP64 (every
+ * range, Payne-Hanek included; plain arguments by a route with shorter polynomials than the FP64 entries need) and
+ * both results are rounded once to float: within 0.5003 ulp of the true values, the correctly rounded float in all
+ * but ~3e-5 of the cases.  NaN/Inf -> 0x7FC00000 in both outputs; |x| <= 2^-27 -> (x, 1.0f).  12 bytes of traffic per
+ * element.  Arrays must be 4-byte aligned; 256-bit accesses are used when the three arrays share one phase modulo
+ * 32 bytes.  The host entry takes device, pinned/registered (processed in place over PCIe) or pageable memory
+ * (staged in 4M-element pieces). */
 int fabe13_sincosf_device(const float* d_in, float* d_sin, float* d_cos, size_t n, void* cuda_stream);
 int fabe13_sincosf_host(const float* in, float* sin_out, float* cos_out, size_t n);
 

@@ -174,18 +174,22 @@ def test_scalar_derived_api_is_the_array_code(fabe13, oracle):
 # ---------------------------------------------------------------------------------------------------------------
 # FP32 arrays (last item): widen, the FP64 core, round once
 # ---------------------------------------------------------------------------------------------------------------
-def test_sincosf_is_the_correctly_rounded_float_result(fabe13):
+def test_sincosf_is_within_half_an_ulp_and_almost_always_correctly_rounded(fabe13):
+    """Our own contract for the FP32 entry (the reference has none): every result within 0.5003 ulp (float) of the true
+    value; equal to the correctly rounded float except in a ~3e-5 fraction of the cases (then 1 ulp away)."""
     rng = np.random.default_rng(5)
-    x = np.concatenate([rng.uniform(-1e4, 1e4, 400_000), rng.uniform(-4, 4, 200_000),
+    x = np.concatenate([rng.uniform(-1e4, 1e4, 400_000), rng.uniform(-4, 4, 200_000), rng.uniform(-3e13, 3e13, 100_000),
                         np.ldexp(rng.uniform(-2, 2, 200_000), rng.integers(-140, 128, 200_000))]).astype(np.float32)
-    s, c = fabe13.host_sincosf(x)
     xd = x.astype(np.float64)
-    ws, wc = np.sin(xd).astype(np.float32), np.cos(xd).astype(np.float32)   # glibc double (<= 1 ulp of double), rounded once
-    # identical except where the two double values straddle a float rounding boundary: at most a handful, 1 ulp apart
-    for got, want in ((s, ws), (c, wc)):
-        diff = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
-        assert diff.max() <= 1 and np.count_nonzero(diff) <= 3
-    assert np.all(np.abs(s.astype(np.float64) - np.sin(xd)) <= 0.5000001 * np.spacing(np.abs(s)).astype(np.float64) + 1e-45)
+    true = {"sin": np.sin(xd), "cos": np.cos(xd)}                              # glibc double: <= 1 ulp of double
+    for core, budget in ((0, 2e-4), (1, 1e-6)):                                # psi core: the full FP64 routine
+        s, c = fabe13.host_sincosf(x, core)
+        for got, t in ((s, true["sin"]), (c, true["cos"])):
+            want = t.astype(np.float32)
+            diff = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+            assert diff.max() <= 1 and np.count_nonzero(diff) <= max(3, budget * x.size)
+            ulp = np.spacing(np.abs(want)).astype(np.float64)
+            assert (np.abs(got.astype(np.float64) - t) / ulp).max() <= 0.5003
 
 
 def test_sincosf_specials(fabe13):
