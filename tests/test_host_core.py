@@ -201,3 +201,17 @@ def test_sincosf_specials(fabe13):
     assert s[5] == x[5] and c[5] == 1.0 and s[6] == x[6] and c[6] == 1.0         # tiny: (x, 1) bit for bit
     big = x[7:].astype(np.float64)
     assert np.array_equal(s[7:], np.sin(big).astype(np.float32)) and np.array_equal(c[7:], np.cos(big).astype(np.float32))
+
+
+def test_constants_header_is_what_the_generator_produces(tmp_path):
+    """fabe13_constants.h is generated (tools/gen_constants.py: Remez fits in 80-digit arithmetic, the 2/pi bit table, the
+    pi/2 splits); the committed header must be byte-identical to a fresh run, i.e. no hand-edited constant."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "constants.h"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_constants.py"), str(out)], check=True, capture_output=True)
+    committed = open(os.path.join(root, "fabe_b200", "csrc", "fabe13_constants.h")).read()
+    assert out.read_text() == committed
