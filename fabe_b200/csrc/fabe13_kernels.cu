@@ -3,27 +3,25 @@
 // Replaces the reference's SIMD array drivers fabe13_sincos_avx512 / _avx2 / _neon (fabe13/fabe13.c:545-614,
 // :469-541, :399-464) and their scalar tail loops (:339-358).  Kernels:
 //
-//   sincos_fused_kernel       the hot path (default).  Same streaming loop as sincos_stream_kernel below, but the
-//                             Payne-Hanek lanes of a tile are compacted into a worklist in the block's SHARED memory
-//                             and reduced by the same block in a second pass over that list (dense warps), right
-//                             after the tile's vector stores: one launch per call, no scratch in HBM, and the 8-byte
-//                             result stores of the second pass merge in L2 with the lines the block has just written.
-//   sincos_stream_kernel      option worklist=1.  Grid-stride loop over tiles of 256*UNROLL 256-bit vectors, tiles taken
-//                             in address order (by default one tile per block, so DRAM sees one advancing window);
-//                             each thread issues LDG.E.NA.256 for its vectors, then two STG.E.EF.256 per vector.
-//                             Per lane: reference-exact k, Cody-Waite, polynomial/Psi core, integer-pipe fix-up.
-//                             24 B/element of HBM traffic, no shared memory.  Lanes with |x| >= 2^45 are found with
-//                             a warp ballot, stash x in their sin slot and append their index to a compacted,
-//                             segmented worklist (one atomic per warp that has any).
-//   sincos_second_pass_kernel one Payne-Hanek reduction per worklist entry, lanes densely packed; if a worklist
-//                             segment overflowed it also rescans the sin array for stashed arguments (a finite
-//                             value >= 2^45 can never be a sine) and reduces those in place.
-//   sincos_inline_kernel      small n: one launch, every path inline.
-//   zero_counters_kernel      clears the worklist header; first of the three launches of a large call, the other two
+//   sincos_fused_kernel       the hot path.  Tiles of 256*UNROLL 256-bit vectors in address order (by default one
+//                             tile per block, so DRAM sees one advancing window); each thread issues LDG.E.NA.256 for
+//                             its vectors, then two STG.E.EF.256 per vector.  Per lane: reference-exact k, Cody-Waite,
+//                             polynomial/Psi core, integer-pipe rotation.  24 B/element of HBM traffic.  Lanes with
+//                             |x| >= 2^45 are found with warp votes and reduced by Payne-Hanek in the same kernel:
+//                             a dense warp runs the every-range routine for all its lanes; otherwise the warp compacts
+//                             such lanes into its slice of shared memory and strides over that list with all lanes
+//                             busy; a warp with only 1-3 of them (hybrid launches) appends them to a global worklist.
+//   sincos_second_pass_kernel the global worklist: one Payne-Hanek reduction per entry, lanes densely packed; if a
+//                             segment overflowed (option worklist=1 only) it also rescans the output for arguments
+//                             still parked there (a finite value >= 2^45 can never be a sine).
+//   sincos_inline_kernel      small n: one launch, one element per thread, every path inline.
+//   sincosf_kernel            FP32 arrays: FP64 arithmetic inside, 12 B/element.
+//   zero_counters_kernel      clears the worklist header; first of the three launches of a hybrid call, the other two
 //                             follow it with programmatic dependent launch.
 //
-// Data layout in HBM: three contiguous FP64 arrays (in, sin, cos), optional int64 k array (test hook), and a
-// workspace = { kSegments counters, 128 B apart } { kSegments x seg_cap u32 element indices }.
+// Data layout in HBM: three contiguous FP64 arrays (in, sin, cos), optional int64 k array (test hook), and -- only
+// for launches that use the global worklist -- a workspace = { kSegments counters, 128 B apart }
+// { kSegments x seg_cap u32 element indices }.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -87,6 +85,9 @@ struct StreamArgs {
     uint32_t ntiles;   // tiles of kThreads*UNROLL vectors
     uint32_t tiles_per_block;  // consecutive tiles one block takes per grid-stride step
     bool pdl;                  // launched with programmatic stream serialisation
+    uint32_t local_min;        // warps with at least this many Payne-Hanek lanes reduce them locally (kLocalMin;
+                               // 0xFFFFFFFF = never: everything goes to the global worklist, option worklist=1)
+    uint32_t dense_hint;       // first-element votes (of 32) that send a warp down the dense route (kDenseHint; 33 = never)
     Worklist wl;
 };
 
@@ -128,31 +129,6 @@ __device__ __forceinline__ void store_stream<1>(void* p, const uint64_t (&b)[1])
 // 2^45 <= |v| < Inf: an argument parked in the sin array by the first pass (no sine has that magnitude)
 __device__ __forceinline__ bool is_stashed(uint64_t bits) { return fabe13_is_huge(fabe13_abs_hi(bits)); }
 
-// ---- one lane of the fast path.  Returns false for lanes that took an override (tiny, NaN/Inf, or Payne-Hanek
-//      range); a lane in the Payne-Hanek range leaves x itself in its sin slot (the second pass reads it back from
-//      there, so in-place calls stay correct).
-template <int CORE, bool WITH_K, int OUT>
-__device__ __forceinline__ bool fast_lane(uint64_t xb, uint64_t& sb, uint64_t& cb, long long& k) {
-    const double x = __longlong_as_double((long long)xb);
-    double biased;
-    const double kd = fabe13_quadrant_index(x, &biased);
-    const double r = fabe13_cody_waite(x, kd);
-    double sr, cr;
-    fabe13_core<CORE>(r, &sr, &cr);
-    const uint32_t ahi = fabe13_abs_hi(xb);
-    if (out_derived(OUT)) {
-        // complete fix-up (tiny -> (x, 1), NaN/Inf -> qNaN), the division, then park x for the Payne-Hanek pass
-        uint64_t s0, c0;
-        fabe13_fixup<FABE13_STASH_NONE>(xb, sr, cr, fabe13_q_from_biased(biased), &s0, &c0);
-        sb = fabe13_is_huge(ahi) ? xb : fabe13_derived<OUT>(xb, s0, c0);
-        cb = 0;
-    } else {
-        fabe13_fixup<(OUT == OUT_COS) ? FABE13_STASH_COS : FABE13_STASH_SIN>(xb, sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
-    }
-    if (WITH_K) k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
-    return fabe13_is_plain(ahi);
-}
-
 // ---- the fused kernel's form of the fast path: the quadrant rotation only, NO overrides.  For ordinary data no
 //      lane needs one, and the warp finds that out with the vote it takes anyway -- so the override selects (and the
 //      values they select from) leave the hot path: ~7 of 62 instructions per element.  A warp that does hold a tiny,
@@ -188,123 +164,8 @@ __device__ __forceinline__ void patch_lane(uint64_t xb, uint64_t& sb, uint64_t& 
     }
 }
 
-// Append this warp's flagged elements (`mine` per lane, indices produced by `emit`) to the block's worklist segment:
-// a warp prefix sum, one atomic for the whole warp, then each lane writes its own run of slots.
-template <typename Emit>
-__device__ __forceinline__ void worklist_push(uint32_t mine, const Worklist& wl, uint32_t lane, Emit emit) {
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if ((int)lane >= d) incl += t;
-    }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (total == 0) return;
-    grid_dependency_wait();  // the counters must have been zeroed (the stream kernel may have been launched early)
-    const uint32_t seg = blockIdx.x % kSegments;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(wl.counters + seg * kCounterStrideWords, total);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    emit(wl.entries + (size_t)seg * wl.seg_cap, base + incl - mine);
-}
-
-template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
-__global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArgs a) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const double* in = a.in + a.head;
-    double* so = out_first(OUT) ? a.sin_out + a.head : nullptr;
-    double* co = out_second(OUT) ? a.cos_out + a.head : nullptr;
-
-    // grid-stride over chunks of tiles_per_block consecutive tiles; trip counts are block-uniform, so the ballots
-    // below always see full warps
-    for (uint32_t chunk = blockIdx.x; chunk * a.tiles_per_block < a.ntiles; chunk += gridDim.x) {
-        const uint32_t tile_end = min(a.ntiles, (chunk + 1) * a.tiles_per_block);
-        for (uint32_t tile = chunk * a.tiles_per_block; tile < tile_end; ++tile) {
-            const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
-            uint64_t xb[UNROLL][VEC];
-            bool live[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t v = v0 + u * kThreads;
-                live[u] = v < a.nvec;
-                if (live[u]) {
-                    load_stream<VEC>(in + (size_t)v * VEC, xb[u]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) xb[u][j] = 0x3FF0000000000000ull;  // 1.0: a plain lane
-                }
-            }
-            bool all_plain = true;
-            uint64_t sb[UNROLL][VEC], cb[UNROLL][VEC];
-            long long kk[UNROLL][VEC];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) all_plain &= fast_lane<CORE, WITH_K, OUT>(xb[u][j], sb[u][j], cb[u][j], kk[u][j]);
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                if (live[u]) {
-                    const size_t e = (size_t)(v0 + u * kThreads) * VEC;
-                    if (out_first(OUT)) store_stream<VEC>(so + e, sb[u]);
-                    if (out_second(OUT)) store_stream<VEC>(co + e, cb[u]);
-                    if (WITH_K) {
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) a.k_out[a.head + e + j] = kk[u][j];
-                    }
-                }
-            }
-            // warp ballot: which lanes hold anything but plain arguments?  (zero for ordinary data: one VOTE per tile)
-            if (__ballot_sync(0xFFFFFFFFu, !all_plain) != 0) {  // rare: tiny, special or Payne-Hanek-range lanes
-                uint32_t n_huge = 0;
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
-                }
-                if (__ballot_sync(0xFFFFFFFFu, n_huge != 0) != 0) {  // compact the Payne-Hanek lanes of this warp
-                    worklist_push(n_huge, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
-#pragma unroll
-                        for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) {
-                                if (is_stashed(xb[u][j])) {
-                                    if (slot < a.wl.seg_cap) seg_entries[slot] = a.head + (v0 + u * kThreads) * VEC + j;
-                                    ++slot;
-                                }
-                            }
-                        }
-                    });
-                }
-            }
-        }
-    }
-
-    // edges: the < VEC elements in front of the aligned body and the < VEC behind it (block 0, first warp)
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        const uint32_t body_end = a.head + a.nvec * VEC;
-        const uint32_t n_edge = a.head + (a.n - body_end);
-        const bool on = lane < n_edge;
-        const uint32_t idx = lane < a.head ? lane : body_end + (lane - a.head);
-        uint64_t xb = 0x3FF0000000000000ull, sb, cb;
-        long long k = 0;
-        if (on) xb = (uint64_t)__double_as_longlong(a.in[idx]);
-        fast_lane<CORE, WITH_K, OUT>(xb, sb, cb, k);
-        const bool huge = is_stashed(xb);
-        if (on) {
-            if (out_first(OUT)) a.sin_out[idx] = __longlong_as_double((long long)sb);
-            if (out_second(OUT)) a.cos_out[idx] = __longlong_as_double((long long)cb);
-            if (WITH_K) a.k_out[idx] = k;
-        }
-        worklist_push(huge ? 1u : 0u, a.wl, lane, [&](uint32_t* seg_entries, uint32_t slot) {
-            if (huge && slot < a.wl.seg_cap) seg_entries[slot] = idx;
-        });
-    }
-}
-
-
 // ---- the default hot path: streaming tile + warp-local worklist (+ global worklist for stragglers) --------------
-// Phase 1 is the streaming tile of sincos_stream_kernel: every lane runs the fast path and the vectors are stored
+// Phase 1 is the streaming tile: every lane runs the fast path and the vectors are stored
 // (a Payne-Hanek lane parks x itself in its output slot).  One warp ballot per tile says whether any lane was not
 // plain; only then (rare for ordinary data) the warp counts its Payne-Hanek lanes and
 //   * count >= kLocalMin: compacts (x, offset-in-tile) pairs into its own slice of shared memory and strides over
@@ -312,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) sincos_stream_kernel(const StreamArg
 //     with the lines the warp has just written.  No block-wide barrier, no scratch in HBM, cost proportional to
 //     the number of such lanes (rounded up to 32 per warp);
 //   * count < kLocalMin (sparse stragglers; hybrid launches only): appends their indices to the global worklist
-//     exactly like sincos_stream_kernel, and the second-pass kernel reduces them densely packed.  A lone lane would
+//     (one atomic per warp on one of 32 counters), and the second-pass kernel reduces them densely packed.  A lone lane would
 //     otherwise cost the warp a whole ~250-instruction round at 1/32 utilisation and, worse, keep the block's
 //     registers and shared memory occupied while it runs (throughput here follows occupancy closely: 5 instead of
 //     6 resident blocks costs 25 %).  At most kLocalMin-1 of a warp's 128 elements are ever pushed, so the global
@@ -419,7 +280,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
     // (Payne-Hanek vs Cody-Waite) and share core and fix-up; a round in which no lane holds a Payne-Hanek argument
     // skips that branch altogether, so interleaved data (every 4th element huge, say) costs one such reduction
     // per tile, not four.  A wrong guess costs nothing but time: the routine is complete for every input.
-    if (__popc(__ballot_sync(0xFFFFFFFFu, !fabe13_is_plain(fabe13_abs_hi(xb[0][0])))) >= (int)kDenseHint) {
+    if (__popc(__ballot_sync(0xFFFFFFFFu, !fabe13_is_plain(fabe13_abs_hi(xb[0][0])))) >= (int)a.dense_hint) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
@@ -480,7 +341,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
             }
             const uint32_t count = __shfl_sync(0xFFFFFFFFu, incl, 31);
             uint32_t slot = incl - n_huge;
-            if (count >= kLocalMin || a.wl.counters == nullptr) {
+            if (count >= a.local_min || a.wl.counters == nullptr) {
                 // compact this warp's Payne-Hanek lanes into its shared-memory list ...
                 stage_stream_warp(s_table[warp], lane);
 #pragma unroll
@@ -788,23 +649,21 @@ cudaError_t launch_1arg(void (*kernel)(Arg), const Arg& arg, int grid, int block
 }
 
 template <int CORE, int VEC, bool WITH_K, int OUT>
-cudaError_t launch_stream_unroll(const StreamArgs& a, bool fused, int unroll, int grid, cudaStream_t stream) {
-    if (fused) {
+cudaError_t launch_stream_unroll(const StreamArgs& a, int unroll, int grid, cudaStream_t stream) {
+    {
         const bool one_tile = (uint32_t)grid == a.ntiles && a.tiles_per_block == 1;
         if (unroll == 2) return launch_1arg(sincos_fused_kernel<CORE, VEC, 2, WITH_K, OUT, false>, a, grid, kThreads, stream, a.pdl);
         if (one_tile) return launch_1arg(sincos_fused_kernel<CORE, VEC, 1, WITH_K, OUT, true>, a, grid, kThreads, stream, a.pdl);
         return launch_1arg(sincos_fused_kernel<CORE, VEC, 1, WITH_K, OUT, false>, a, grid, kThreads, stream, a.pdl);
     }
-    if (unroll == 2) return launch_1arg(sincos_stream_kernel<CORE, VEC, 2, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
-    return launch_1arg(sincos_stream_kernel<CORE, VEC, 1, WITH_K, OUT>, a, grid, kThreads, stream, a.pdl);
 }
 
 template <int CORE, bool WITH_K, int OUT>
-cudaError_t launch_stream_vec(const StreamArgs& a, bool fused, int vec, int unroll, int grid, cudaStream_t stream) {
+cudaError_t launch_stream_vec(const StreamArgs& a, int vec, int unroll, int grid, cudaStream_t stream) {
     switch (vec) {
-        case 4: return launch_stream_unroll<CORE, 4, WITH_K, OUT>(a, fused, unroll, grid, stream);
-        case 2: return launch_stream_unroll<CORE, 2, WITH_K, OUT>(a, fused, unroll, grid, stream);
-        default: return launch_stream_unroll<CORE, 1, WITH_K, OUT>(a, fused, unroll, grid, stream);
+        case 4: return launch_stream_unroll<CORE, 4, WITH_K, OUT>(a, unroll, grid, stream);
+        case 2: return launch_stream_unroll<CORE, 2, WITH_K, OUT>(a, unroll, grid, stream);
+        default: return launch_stream_unroll<CORE, 1, WITH_K, OUT>(a, unroll, grid, stream);
     }
 }
 
@@ -821,16 +680,16 @@ cudaError_t launch_stream_unroll_derived(const StreamArgs& a, int vec, int grid,
 }
 
 template <int CORE>
-cudaError_t launch_stream(const StreamArgs& a, int op, bool fused, int vec, int unroll, int grid, cudaStream_t stream) {
+cudaError_t launch_stream(const StreamArgs& a, int op, int vec, int unroll, int grid, cudaStream_t stream) {
     // derived functions: fused kernel only, one vector in flight per thread (unroll 1)
     if (op == FABE13_OP_TAN) return launch_stream_unroll_derived<CORE, OUT_TAN>(a, vec, grid, stream);
     if (op == FABE13_OP_COT) return launch_stream_unroll_derived<CORE, OUT_COT>(a, vec, grid, stream);
     if (op == FABE13_OP_SINC) return launch_stream_unroll_derived<CORE, OUT_SINC>(a, vec, grid, stream);
     if (a.sin_out && a.cos_out)
-        return a.k_out ? launch_stream_vec<CORE, true, OUT_BOTH>(a, fused, vec, unroll, grid, stream)
-                       : launch_stream_vec<CORE, false, OUT_BOTH>(a, fused, vec, unroll, grid, stream);
-    if (a.sin_out) return launch_stream_vec<CORE, false, OUT_SIN>(a, fused, vec, unroll, grid, stream);
-    return launch_stream_vec<CORE, false, OUT_COS>(a, fused, vec, unroll, grid, stream);
+        return a.k_out ? launch_stream_vec<CORE, true, OUT_BOTH>(a, vec, unroll, grid, stream)
+                       : launch_stream_vec<CORE, false, OUT_BOTH>(a, vec, unroll, grid, stream);
+    if (a.sin_out) return launch_stream_vec<CORE, false, OUT_SIN>(a, vec, unroll, grid, stream);
+    return launch_stream_vec<CORE, false, OUT_COS>(a, vec, unroll, grid, stream);
 }
 
 // Which Payne-Hanek worklist a launch over n elements uses (LaunchTuning::worklist; 0 = pick by size).
@@ -854,9 +713,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
                         const LaunchTuning& t, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                         int* launches) {
     int mode = worklist_mode(n, t);
-    if (op != FABE13_OP_SINCOS && mode == WL_GLOBAL) mode = WL_HYBRID;  // derived functions exist in the fused kernel only
     if (mode != WL_LOCAL && workspace == nullptr) mode = WL_LOCAL;  // no scratch: everything stays in the block
-    const bool fused = mode != WL_GLOBAL;
     if (n < (size_t)t.small_n) {
         const long long need = (long long)((n + kThreads - 1) / kThreads);
         const long long cap = (long long)dev.sm_count * 64;
@@ -897,13 +754,17 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     if (t.blocks_per_sm > 0 && grid > (long long)dev.sm_count * t.blocks_per_sm) grid = (long long)dev.sm_count * t.blocks_per_sm;
     if (grid < 1) grid = 1;
 
+    // worklist=1 sends every Payne-Hanek lane to the global list: no local reduction, no dense route
+    a.local_min = mode == WL_GLOBAL ? 0xFFFFFFFFu : kLocalMin;
+    a.dense_hint = mode == WL_GLOBAL ? 33u : kDenseHint;
+
     if (mode == WL_LOCAL) {  // one launch, no scratch
         a.wl.counters = nullptr;
         a.wl.entries = nullptr;
         a.wl.seg_cap = 0;
         a.pdl = false;
         *launches += 1;
-        return launch_stream<CORE>(a, op, true, vec, unroll, (int)grid, stream);
+        return launch_stream<CORE>(a, op, vec, unroll, (int)grid, stream);
     }
 
     // global or hybrid: zero the counters -> streaming kernel -> second pass over the global worklist
@@ -920,7 +781,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
         err = cudaMemsetAsync(workspace, 0, kWorklistHeaderBytes, stream);
     }
     if (err != cudaSuccess) return err;
-    err = launch_stream<CORE>(a, op, fused, vec, unroll, (int)grid, stream);
+    err = launch_stream<CORE>(a, op, vec, unroll, (int)grid, stream);
     if (err != cudaSuccess) return err;
 
     SecondPassArgs b;
