@@ -143,7 +143,7 @@ __device__ __forceinline__ bool plain_lane(uint64_t xb, uint64_t& sb, uint64_t& 
     fabe13_core<CORE>(r, &sr, &cr);
     const uint32_t ahi = fabe13_abs_hi(xb);
     fabe13_rotate(sr, cr, fabe13_q_from_biased(biased), &sb, &cb);
-    if (out_derived(OUT)) sb = fabe13_derived<OUT>(xb, sb, cb);
+    if (out_derived(OUT)) sb = fabe13_derived_plain<OUT>(xb, sb, cb);  // (lanes that are not plain are patched later)
     if (WITH_K) k = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
     return fabe13_is_plain(ahi);
 }
