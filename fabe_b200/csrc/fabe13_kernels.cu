@@ -425,7 +425,6 @@ struct SecondPassArgs {
     double* cos_out;
     long long* k_out;
     uint32_t n;
-    int op;            // FABE13_OP_SINCOS, or the derived function whose values go to sin_out
     Worklist wl;
 };
 
@@ -433,7 +432,6 @@ template <int CORE>
 __device__ __forceinline__ void reduce_stashed(const SecondPassArgs& a, uint32_t idx, uint64_t xb, const uint32_t* table) {
     uint64_t sb, cb;
     const int q = fabe13_sincos_huge<CORE>(xb, table, &sb, &cb);  // the caller has checked is_stashed(xb)
-    if (a.op != FABE13_OP_SINCOS) sb = fabe13_derived_rt(a.op, xb, sb, cb);
     if (a.sin_out) a.sin_out[idx] = __longlong_as_double((long long)sb);
     if (a.cos_out) a.cos_out[idx] = __longlong_as_double((long long)cb);
     if (a.k_out) a.k_out[idx] = q;
@@ -713,6 +711,9 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
                         const LaunchTuning& t, const DeviceInfo& dev, void* workspace, cudaStream_t stream,
                         int* launches) {
     int mode = worklist_mode(n, t);
+    // tan, cot and sinc keep their Payne-Hanek lanes in the block at every size: the global list's overflow rescan
+    // recognises a parked argument by its magnitude (no sine or cosine reaches 2^45), and a tangent can
+    if (op != FABE13_OP_SINCOS) mode = WL_LOCAL;
     if (mode != WL_LOCAL && workspace == nullptr) mode = WL_LOCAL;  // no scratch: everything stays in the block
     if (n < (size_t)t.small_n) {
         const long long need = (long long)((n + kThreads - 1) / kThreads);
@@ -789,7 +790,6 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     b.cos_out = d_cos;
     b.k_out = d_k;
     b.n = (uint32_t)n;
-    b.op = op;
     b.wl = a.wl;
     err = launch_1arg(sincos_second_pass_kernel<CORE>, b, dev.sm_count * t.second_pass_blocks_per_sm, kThreads, stream, a.pdl);
     *launches += a.pdl ? 3 : 2;
@@ -798,7 +798,7 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
 
 }  // namespace
 
-size_t workspace_bytes(size_t n, const LaunchTuning& t) {
+size_t workspace_bytes(size_t n, const LaunchTuning& t) {  // (an upper bound: the derived functions never need any)
     const int mode = worklist_mode(n, t);
     if (mode == WL_LOCAL) return 0;  // the warp-local worklists live in shared memory
     return (size_t)kWorklistHeaderBytes + (size_t)kSegments * segment_capacity(n, t, mode) * sizeof(uint32_t);

@@ -44,7 +44,8 @@ def gpu_sincos(fabe13, cuda, x):
 # heaviest cases run in the default mode only; the tests of the global worklist's own machinery (capacity/overflow
 # rescan, PDL, caller workspace) are skipped where no global worklist exists.
 HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay",
-         "test_sincosf_device_matches_host_bit_for_bit", "test_sincosf_host_entries", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
+         "test_sincosf_device_matches_host_bit_for_bit", "test_sincosf_host_entries",
+         "test_cot_of_tiny_arguments_is_not_mistaken_for_a_parked_argument", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
          "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
          "test_mixed_host_device_pointers_fail_loudly", "test_native_library_is_the_one_running"}
 GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
@@ -603,6 +604,27 @@ def test_tan_cot_sinc_device(fabe13, cuda, oracle, small_n, core):
     body = np.isfinite(x) & (np.abs(x) > 1e-6)
     t = fabe13.tan_array(xt).cpu().numpy()
     assert (np.abs(t[body] - (ls / lc)[body]) / np.abs((ls / lc)[body])).max() < (1e-15 if core == 0 else 5e-15)  # psi core: 4.4e-16 per value
+
+
+@pytest.mark.parametrize("worklist,shift", [(1, 20), (1, 3), (3, 3)])
+def test_cot_of_tiny_arguments_is_not_mistaken_for_a_parked_argument(fabe13, cuda, worklist, shift):
+    """cot(x) = 1/x for tiny x is a finite value above 2^45 -- exactly what the global worklist's overflow rescan takes
+    for an argument parked by the first pass.  The derived functions therefore never use the global list (found by the
+    soak: worklist=1 on a half-tiny, half-huge array overflowed the list and the rescan 'reduced' legitimate results)."""
+    import torch
+
+    fabe13.set_option("worklist", worklist)
+    fabe13.set_option("worklist_shift", shift)
+    fabe13.set_option("small_n", 0)
+    fabe13.set_option("hybrid_min_n", 0)
+    rng = np.random.default_rng(3)
+    n = 500_003
+    x = np.ldexp(rng.uniform(-2, 2, n), rng.integers(-1074, 1024, n))
+    xt = torch.from_numpy(x).to(cuda)
+    for op, fn in ((fabe13.OP_COT, fabe13.cot_array), (fabe13.OP_TAN, fabe13.tan_array), (fabe13.OP_SINC, fabe13.sinc_array)):
+        got = fn(xt)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(got.cpu().numpy()), bits(fabe13.host_derived(x, op))), f"op {op}"
 
 
 @pytest.mark.parametrize("n", [7, 50_000, 3_000_000, 20_000_001])

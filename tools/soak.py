@@ -87,6 +87,10 @@ def main():
             fn(xv, out=xv)
             torch.cuda.synchronize()
             ok = np.array_equal(bits(o.cpu().numpy()), bits(want)) and np.array_equal(bits(xv.cpu().numpy()), bits(want))
+            if not ok:
+                bad_i = np.nonzero(bits(o.cpu().numpy()) != bits(want))[0]
+                for i in bad_i[:5]:
+                    print(f"  derived op {op}: i={i} x={x[i]!r} ({x[i].hex()}) got {o[i].item()!r} want {want[i]!r}", flush=True)
             if n < 3_000_000:
                 ok = ok and np.array_equal(bits(fn(x)), bits(want))
         elif mode == 3:  # pageable host
