@@ -52,7 +52,7 @@ def main():
             fb.set_option(k, v)
         x = make_input(rng, n)
         hs, hc, hk = fb.host_core(x, opts["core"])
-        mode = int(rng.integers(0, 7))
+        mode = int(rng.integers(0, 8))
         off_in, off_s, off_c = (int(v) for v in rng.integers(0, 4, 3))
         if rng.random() < 0.5:
             off_s = off_c = off_in
@@ -93,6 +93,26 @@ def main():
                     print(f"  derived op {op}: i={i} x={x[i]!r} ({x[i].hex()}) got {o[i].item()!r} want {want[i]!r}", flush=True)
             if n < 3_000_000:
                 ok = ok and np.array_equal(bits(fn(x)), bits(want))
+        elif mode == 7:  # FP32 arrays: device (every mutual alignment, in place) and host
+            xf = x.astype(np.float32)
+            if rng.random() < 0.3:
+                xf = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32).view(np.float32).copy()
+            ws, wc = fb.host_sincosf(xf, opts["core"])
+            bx = torch.zeros(n + 16, dtype=torch.float32, device=dev)
+            bs = torch.zeros(n + 16, dtype=torch.float32, device=dev)
+            bc = torch.zeros(n + 16, dtype=torch.float32, device=dev)
+            o_in, o_s, o_c = (int(v) for v in rng.integers(0, 9, 3))
+            if rng.random() < 0.6:
+                o_s = o_c = o_in
+            bx[o_in:o_in + n] = torch.from_numpy(xf).to(dev)
+            fb.sincosf(bx[o_in:o_in + n], out_sin=bs[o_s:o_s + n], out_cos=bc[o_c:o_c + n])
+            torch.cuda.synchronize()
+            u32 = lambda a: np.ascontiguousarray(a).view(np.uint32)
+            ok = np.array_equal(u32(bs[o_s:o_s + n].cpu().numpy()), u32(ws)) and np.array_equal(u32(bc[o_c:o_c + n].cpu().numpy()), u32(wc))
+            ok = ok and float(bs[:o_s].abs().sum()) == 0 and float(bs[o_s + n:].abs().sum()) == 0
+            if n < 3_000_000:
+                hs_, hc_ = fb.sincosf(xf)
+                ok = ok and np.array_equal(u32(hs_), u32(ws)) and np.array_equal(u32(hc_), u32(wc))
         elif mode == 3:  # pageable host
             s, c = fb.sincos(x)
             ok = np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
