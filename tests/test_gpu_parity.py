@@ -914,6 +914,19 @@ def test_more_than_one_launch_sequence(fabe13, cuda, oracle):
         v = (s[sl] * s[sl] + c[sl] * c[sl] - 1.0).abs()
         worst = max(worst, torch.nan_to_num(v, nan=0.0).max().item())
     assert worst <= 6e-16, worst
+    del s, c
+    # the single-output, derived and FP32 entries split the same way
+    t = fabe13.tan_array(x)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(t[idx].cpu().numpy()), bits(fabe13.host_derived(xs, fabe13.OP_TAN)))
+    del t
+    xf = x.to(torch.float32)
+    del x
+    sf, cf = fabe13.sincosf(xf)
+    torch.cuda.synchronize()
+    ws, wc = fabe13.host_sincosf(xf[idx].cpu().numpy())
+    assert np.array_equal(sf[idx].cpu().numpy().view(np.uint32), ws.view(np.uint32))
+    assert np.array_equal(cf[idx].cpu().numpy().view(np.uint32), wc.view(np.uint32))
 
 
 @pytest.mark.parametrize("small_n", [0, 1 << 30])
