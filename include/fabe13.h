@@ -43,7 +43,9 @@ const char* fabe13_get_active_implementation_name(void);
 int fabe13_get_active_simd_width(void);
 
 /* Scalar functions (host).  sin/cos use the per-element core of the array path; sinc/tan/cot are derived from it
- * with the reference's guards (|x| < 1e-9 -> 1; cos == 0 -> NaN; sin == 0 -> NaN); atan/asin/acos forward to libm. */
+ * with the reference's guards (|x| < 1e-9 -> 1; cos == 0 -> NaN; sin == 0 -> NaN) and one IEEE division -- the same
+ * code the array forms in fabe13_cuda.h compile for the device; every NaN they return is the canonical quiet NaN
+ * (the reference propagates whatever NaN the division makes).  atan/asin/acos forward to libm. */
 double fabe13_sin(double x);
 double fabe13_cos(double x);
 double fabe13_sinc(double x);
