@@ -5,6 +5,7 @@ roadmap item README.md:227).  Importing this module registers
     torch.ops.fabe13.sin(Tensor x) -> Tensor        torch.ops.fabe13.cos(Tensor x) -> Tensor
     torch.ops.fabe13.tan(Tensor x) -> Tensor        torch.ops.fabe13.cot(Tensor x) -> Tensor
     torch.ops.fabe13.sinc(Tensor x) -> Tensor       (unnormalised: sin(x)/x, 1 for |x| < 1e-9, as the reference's)
+    torch.ops.fabe13.sincosf(Tensor x) -> (Tensor sin, Tensor cos)      float32 tensors
 
 for float64 tensors: CUDA tensors go to fabe13_sincos_device on the current stream, CPU tensors to fabe13_sincos_host.
 Non-contiguous inputs are made contiguous first.  The operators carry fake (meta) implementations, so they trace
@@ -67,6 +68,17 @@ def register():
 
     def sinc(x: torch.Tensor) -> torch.Tensor:
         return api.sinc_array(_prep(x)).view(x.shape)
+
+    @torch.library.custom_op("fabe13::sincosf", mutates_args=())
+    def sincosf(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        if x.dtype != torch.float32:
+            raise TypeError("fabe13::sincosf takes float32 tensors")
+        s, c = api.sincosf(x.contiguous())
+        return s.view(x.shape), c.view(x.shape)
+
+    @sincosf.register_fake
+    def _(x):
+        return torch.empty_like(x, memory_format=torch.contiguous_format), torch.empty_like(x, memory_format=torch.contiguous_format)
 
     single("tan", tan)
     single("cot", cot)

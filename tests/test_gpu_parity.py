@@ -718,6 +718,10 @@ def test_torch_ops_registration(fabe13, cuda, oracle):
         for op, name in ((fabe13.OP_TAN, "tan"), (fabe13.OP_COT, "cot"), (fabe13.OP_SINC, "sinc")):
             got = getattr(torch.ops.fabe13, name)(xt)
             assert np.array_equal(bits(got.cpu().numpy().ravel()), bits(fabe13.host_derived(x.ravel(), op)))
+        sf, cf = torch.ops.fabe13.sincosf(xt.to(torch.float32))
+        ws, wc = fabe13.host_sincosf(x.ravel().astype(np.float32))
+        assert np.array_equal(sf.cpu().numpy().ravel().view(np.uint32), ws.view(np.uint32))
+        assert np.array_equal(cf.cpu().numpy().ravel().view(np.uint32), wc.view(np.uint32))
 
 
 @pytest.mark.parametrize("core", [0, 1])
