@@ -217,8 +217,14 @@ int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k,
                 if (user_ws_bytes < need) return record(cudaErrorInvalidValue, "workspace too small");
                 ws = user_ws;
             } else {
-                FABE13_TRY(cudaMallocFromPoolAsync(&ws, need, ds->pool, stream));
-                pooled = true;
+                // no scratch to be had (device memory exhausted by the caller's own arrays): not an error -- without
+                // a workspace the launch keeps every Payne-Hanek lane in the block (worklist design 2)
+                if (cudaMallocFromPoolAsync(&ws, need, ds->pool, stream) == cudaSuccess) {
+                    pooled = true;
+                } else {
+                    (void)cudaGetLastError();
+                    ws = nullptr;
+                }
             }
         }
         int launches = 0;
@@ -348,8 +354,10 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
     int launches = 0;
     void* ws = nullptr;
     const size_t need_ws = n >= (size_t)t.small_n ? fabe13::workspace_bytes(n, t) : 0;
-    if (need_ws > 0)  // a global worklist is in play: the launch sequence needs its scratch
-        FABE13_TRY(cudaMallocFromPoolAsync(&ws, need_ws, s.pool, s.small_stream));
+    if (need_ws > 0 && cudaMallocFromPoolAsync(&ws, need_ws, s.pool, s.small_stream) != cudaSuccess) {
+        (void)cudaGetLastError();  // no scratch: the launch keeps every Payne-Hanek lane in the block
+        ws = nullptr;
+    }
     cudaError_t e = fabe13::launch_sincos((const double*)d_in, (double*)d_s, (double*)d_c, nullptr, n, op, core, t, s.info, ws,
                                           s.small_stream, &launches);
     g_launches.fetch_add((unsigned long long)launches);
