@@ -555,32 +555,65 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
         }
         (void)cudaGetLastError();  // registered without a device mapping: stage it like pageable memory
     }
-    const size_t piece = (size_t)1 << 22;  // floats per piece: 3 x 16 MB of pinned staging
-    const size_t need_doubles = (3 * piece * sizeof(float) + sizeof(double) - 1) / sizeof(double);
-    if (ds->small_cap * 3 < need_doubles) {
-        if (ds->small_stage) cudaFreeHost(ds->small_stage);
-        ds->small_stage = nullptr;
-        ds->small_cap = 0;
-        const size_t cap = (need_doubles + 2) / 3;
-        FABE13_TRY(cudaHostAlloc(&ds->small_stage, 3 * cap * sizeof(double), cudaHostAllocDefault));
-        ds->small_cap = cap;
+    // pageable memory: like the FP64 path, worker w owns slot w (its pinned staging buffers and its stream) and the
+    // pieces i = w (mod workers): copy in, one kernel over the staging buffers in place (zero-copy over PCIe), copy out.
+    // The staging copies bound this path (host memory bandwidth), hence the threads.
+    const size_t piece_doubles = (size_t)1 << 20;                 // staging buffers are sized in doubles: 8 MB each
+    const size_t piece = piece_doubles * sizeof(double) / sizeof(float);  // floats per piece
+    const size_t npieces = (n + piece - 1) / piece;
+    int workers = (int)g_cfg.stage_threads.load();
+    if (workers <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned want = hw - hw / 4;
+        workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
     }
-    float* h_in = reinterpret_cast<float*>(ds->small_stage);
-    float* h_s = h_in + piece;
-    float* h_c = h_s + piece;
-    void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
-    FABE13_TRY(cudaHostGetDevicePointer(&d_in, h_in, 0));
-    FABE13_TRY(cudaHostGetDevicePointer(&d_s, h_s, 0));
-    FABE13_TRY(cudaHostGetDevicePointer(&d_c, h_c, 0));
-    for (size_t off = 0; off < n; off += piece) {
-        const size_t m = n - off < piece ? n - off : piece;
-        memcpy(h_in, in + off, m * sizeof(float));
-        if (int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, m, ds->small_stream)) return rc;
-        FABE13_TRY(cudaStreamSynchronize(ds->small_stream));
-        memcpy(sin_out + off, h_s, m * sizeof(float));
-        memcpy(cos_out + off, h_c, m * sizeof(float));
+    if ((size_t)workers > npieces) workers = (int)npieces;
+    const LaunchTuning t = current_tuning();
+    if (int rc = ensure_slots(*ds, piece_doubles, true, t, workers)) return rc;
+    int dev = 0;
+    FABE13_TRY(cudaGetDevice(&dev));
+    std::atomic<int> rc_all{0};
+    auto work = [&](int w) {
+        if (cudaSetDevice(dev) != cudaSuccess) {
+            rc_all.store(record(cudaErrorInvalidDevice, "cudaSetDevice(worker)"));
+            return;
+        }
+        Slot& sl = ds->slots[w];
+        float* h_in = reinterpret_cast<float*>(sl.h_in);
+        float* h_s = reinterpret_cast<float*>(sl.h_sin);
+        float* h_c = reinterpret_cast<float*>(sl.h_cos);
+        void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
+        if (cudaHostGetDevicePointer(&d_in, h_in, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_s, h_s, 0) != cudaSuccess ||
+            cudaHostGetDevicePointer(&d_c, h_c, 0) != cudaSuccess) {
+            rc_all.store(record(cudaErrorInvalidValue, "cudaHostGetDevicePointer(staging)"));
+            return;
+        }
+        for (size_t i = (size_t)w; i < npieces && rc_all.load() == 0; i += (size_t)workers) {
+            const size_t off = i * piece;
+            const size_t m = n - off < piece ? n - off : piece;
+            memcpy(h_in, in + off, m * sizeof(float));
+            int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, m, sl.stream);
+            if (rc == 0) {
+                cudaError_t e = cudaStreamSynchronize(sl.stream);
+                if (e != cudaSuccess) rc = record(e, "wait for piece (worker)");
+            }
+            if (rc != 0) {
+                rc_all.store(rc);
+                return;
+            }
+            memcpy(sin_out + off, h_s, m * sizeof(float));
+            memcpy(cos_out + off, h_c, m * sizeof(float));
+        }
+    };
+    if (workers <= 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
+        work(0);
+        for (std::thread& x : th) x.join();
     }
-    return 0;
+    return rc_all.load();
 }
 
 int cfg_core() {

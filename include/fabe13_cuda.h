@@ -59,7 +59,7 @@ int fabe13_sinc_host(const double* in, double* out, size_t n);
  * inputs), the correctly rounded float in all but 6e-6 of the cases.  NaN/Inf -> 0x7FC00000 in both outputs; |x| <= 2^-27 -> (x, 1.0f).  12 bytes of traffic per
  * element.  Arrays must be 4-byte aligned; 256-bit accesses are used when the three arrays share one phase modulo
  * 32 bytes.  The host entry takes device, pinned/registered (processed in place over PCIe) or pageable memory
- * (staged in 4M-element pieces). */
+ * (staged in 2M-element pieces by the same worker threads as the FP64 path). */
 int fabe13_sincosf_device(const float* d_in, float* d_sin, float* d_cos, size_t n, void* cuda_stream);
 int fabe13_sincosf_host(const float* in, float* sin_out, float* cos_out, size_t n);
 
