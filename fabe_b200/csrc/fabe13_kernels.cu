@@ -178,7 +178,7 @@ __device__ __forceinline__ void patch_lane(uint64_t xb, uint64_t& sb, uint64_t& 
 //     registers and shared memory occupied while it runs (throughput here follows occupancy closely: 5 instead of
 //     6 resident blocks costs 25 %).  At most kLocalMin-1 of a warp's 128 elements are ever pushed, so the global
 //     list cannot overflow its n/32 entries in the default geometry (and the rescan covers any other geometry).
-// Measured crossover (tools/ab_quick.py): a local round costs ~300 ps, a global entry ~100 ps -> kLocalMin = 4.
+// Measured crossover (tools/ab_worklist.py): a local round costs ~300 ps, a global entry ~100 ps -> kLocalMin = 4.
 constexpr uint32_t kLocalMin = 4;
 // lanes (of 32) whose first element must be non-plain for the warp to take the dense route
 constexpr uint32_t kDenseHint = 24;
