@@ -403,7 +403,7 @@ def run_cuda_arm(args):
                          "traffic": (tpe * n_local) if tpe else None,
                          "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": BYTES_PER_ELEM * n_local,
-                         "step_ms_avg": avg_ms, "step_ms_min": min(step_ms),
+                         "step_ms_avg": avg_ms, "step_ms_median": sorted(step_ms)[len(step_ms) // 2], "step_ms_min": min(step_ms),
                          "note": "duration = CUDA events around one step on the launching stream (the fused streaming kernel; "
                                  "from 2^26 elements per rank on also the counter reset and the second-pass launch, "
                                  "empty for this workload), rank 0"},
