@@ -91,6 +91,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
+        self.mem_samples = []
         self.power_w = []
         self.reason_mask = 0
         self.reasons = set()
@@ -120,6 +121,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.mem_samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
                 self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 self.reason_mask |= int(r)
@@ -142,7 +144,9 @@ class ClockSampler:
         if not self.nv:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
         s = sorted(self.samples)
+        m = sorted(self.mem_samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "mem_mhz": m[len(m) // 2] if m else None,
                 "samples": len(s), "sm_mhz_min": s[0] if s else None, "power_w_max": max(self.power_w) if self.power_w else None,
                 "reason_mask": hex(self.reason_mask)}
 
