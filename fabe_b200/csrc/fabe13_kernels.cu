@@ -10,7 +10,7 @@
 //                             |x| >= 2^45 are found with warp votes and reduced by Payne-Hanek in the same kernel:
 //                             a dense warp runs the every-range routine for all its lanes; otherwise the warp compacts
 //                             such lanes into its slice of shared memory and strides over that list with all lanes
-//                             busy; a warp with only 1-3 of them (hybrid launches) appends them to a global worklist.
+//                             busy; a warp with a lone one (hybrid launches) appends it to a global worklist.
 //   sincos_second_pass_kernel the global worklist: one Payne-Hanek reduction per entry, lanes densely packed; if a
 //                             segment overflowed (option worklist=1 only) it also rescans the output for arguments
 //                             still parked there (a finite value >= 2^45 can never be a sine).
@@ -178,10 +178,11 @@ __device__ __forceinline__ void patch_lane(uint64_t xb, uint64_t& sb, uint64_t& 
 //     registers and shared memory occupied while it runs (throughput here follows occupancy closely: 5 instead of
 //     6 resident blocks costs 25 %).  At most kLocalMin-1 of a warp's 128 elements are ever pushed, so the global
 //     list cannot overflow its n/32 entries in the default geometry (and the rescan covers any other geometry).
-// Measured crossover (tools/ab_worklist.py): a local round costs ~300 ps, a global entry ~100 ps -> kLocalMin = 4.
-constexpr uint32_t kLocalMin = 4;
+// Measured (tools/tune_thresholds.py, profiles/r01_tune_thresholds.md): with the ~150-instruction round of the current
+// reduction only a LONE lane is cheaper on the global list -> kLocalMin = 2 (option local_min).
+constexpr uint32_t kLocalMin = 2;
 // lanes (of 32) whose first element must be non-plain for the warp to take the dense route
-constexpr uint32_t kDenseHint = 24;
+constexpr uint32_t kDenseHint = 16;
 
 // one warp copies the 2/pi word stream into its slice of shared memory (lanes index it by their own exponent; a
 // divergent __constant__ read would serialise)
@@ -700,7 +701,7 @@ int worklist_mode(size_t n, const LaunchTuning& t) {
 }
 
 uint32_t segment_capacity(size_t n, const LaunchTuning& t, int mode) {
-    // hybrid: at most kLocalMin-1 of every 128 elements are pushed -> n/32 entries are plenty
+    // hybrid: at most local_min-1 (default 1) of every 128 elements are pushed -> n/32 entries are plenty
     size_t cap = mode == WL_HYBRID ? n >> 5 : n >> t.worklist_shift;
     if (cap < 4096) cap = 4096;
     return (uint32_t)((cap + kSegments - 1) / kSegments);
@@ -756,8 +757,8 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     if (grid < 1) grid = 1;
 
     // worklist=1 sends every Payne-Hanek lane to the global list: no local reduction, no dense route
-    a.local_min = mode == WL_GLOBAL ? 0xFFFFFFFFu : kLocalMin;
-    a.dense_hint = mode == WL_GLOBAL ? 33u : kDenseHint;
+    a.local_min = mode == WL_GLOBAL ? 0xFFFFFFFFu : (uint32_t)(t.local_min > 0 ? t.local_min : (int)kLocalMin);
+    a.dense_hint = mode == WL_GLOBAL ? 33u : (uint32_t)(t.dense_hint > 0 ? t.dense_hint : (int)kDenseHint);
 
     if (mode == WL_LOCAL) {  // one launch, no scratch
         a.wl.counters = nullptr;

@@ -43,6 +43,8 @@ struct Config {
     std::atomic<long long> core{FABE13_CORE_POLY};
     std::atomic<long long> worklist{0};
     std::atomic<long long> hybrid_min_n{(long long)1 << 26};
+    std::atomic<long long> local_min{2};
+    std::atomic<long long> dense_hint{16};
     std::atomic<long long> blocks_per_sm{0};
     std::atomic<long long> tiles_per_block{1};
     std::atomic<long long> pdl{1};
@@ -72,6 +74,8 @@ const OptionDesc kOptions[] = {
     {"core", "FABE13_CUDA_CORE", &Config::core, 0, 1},
     {"worklist", "FABE13_CUDA_WORKLIST", &Config::worklist, 0, 3},
     {"hybrid_min_n", "FABE13_CUDA_HYBRID_MIN_N", &Config::hybrid_min_n, 0, (long long)1 << 31},
+    {"local_min", "FABE13_CUDA_LOCAL_MIN", &Config::local_min, 1, 129},
+    {"dense_hint", "FABE13_CUDA_DENSE_HINT", &Config::dense_hint, 1, 33},
     {"blocks_per_sm", "FABE13_CUDA_BLOCKS_PER_SM", &Config::blocks_per_sm, 0, 64},
     {"tiles_per_block", "FABE13_CUDA_TILES_PER_BLOCK", &Config::tiles_per_block, 1, 1024},
     {"pdl", "FABE13_CUDA_PDL", &Config::pdl, 0, 1},
@@ -105,6 +109,8 @@ LaunchTuning current_tuning() {
     LaunchTuning t;
     t.worklist = (int)g_cfg.worklist.load();
     t.hybrid_min_n = (int)(g_cfg.hybrid_min_n.load() > 0x7FFFFFFFll ? 0x7FFFFFFFll : g_cfg.hybrid_min_n.load());
+    t.local_min = (int)g_cfg.local_min.load();
+    t.dense_hint = (int)g_cfg.dense_hint.load();
     t.blocks_per_sm = (int)g_cfg.blocks_per_sm.load();
     t.tiles_per_block = (int)g_cfg.tiles_per_block.load();
     t.pdl = (int)g_cfg.pdl.load();

@@ -103,7 +103,8 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
  * "worklist" (where arguments >= 2^45 are reduced: 0 = by size [default]: in the streaming kernel's shared memory,
  * one launch, below "hybrid_min_n" elements, plus a global list for sparse stragglers from there on; 1 = global list
  * and second-pass kernel only [the round-1 design]; 2 = shared memory only at every size; 3 = hybrid at every size),
- * "hybrid_min_n", "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
+ * "hybrid_min_n", "local_min" / "dense_hint" (routing thresholds of the streaming kernel),
+ * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
  * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
  * "zero_copy_max".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
