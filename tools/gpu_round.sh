@@ -23,5 +23,7 @@ tools/abi_bench > ${P}_abi_bench.txt 2>&1
 tools/abi_selfcheck > ${P}_selfcheck.txt 2>&1
 python tools/soak.py 300 7 > ${P}_soak.txt 2>&1
 python tools/accuracy_report.py > ${P}_accuracy.txt 2>&1
+python tools/tune_thresholds.py > ${P}_tune_thresholds.md 2>&1
+python tools/exhaustive_f32.py --device --threads $(nproc) > ${P}_sincosf_exhaustive.txt 2>&1
 [ -x oracle/_ref/fabe13_test_runner_b200 ] && oracle/_ref/fabe13_test_runner_b200 > ${P}_ref_test_runner.txt 2>&1
 tail -c 600 ${P}_bench_c3.json
