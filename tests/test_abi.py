@@ -130,3 +130,16 @@ def test_scalar_api_guards(fabe13):
     assert lib.fabe13_acos(0.3) == math.acos(0.3)
     assert np.isnan(fabe13.sin(float("inf"))) and np.isnan(fabe13.cos(float("nan")))
     assert fabe13.sin(0.0) == 0.0 and np.signbit(fabe13.sin(-0.0)) and fabe13.cos(-0.0) == 1.0
+
+
+def test_both_headers_are_plain_c99_and_cxx11(tmp_path):
+    """The boundary is a C ABI: both public headers compile as strict C99 and as C++11, with no CUDA header in sight."""
+    import subprocess
+
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "fabe13.h"\n#include "fabe13_cuda.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+    text = open(os.path.join(inc, "fabe13_cuda.h")).read() + open(os.path.join(inc, "fabe13.h")).read()
+    assert "cuda_runtime" not in text and "torch" not in text
