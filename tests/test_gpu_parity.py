@@ -785,6 +785,31 @@ def test_sincosf_host_entries(fabe13, cuda, n):
     assert np.array_equal(s2.view(np.uint32), hs.view(np.uint32)) and np.array_equal(c2.view(np.uint32), hc.view(np.uint32))
 
 
+def test_own_known_answer_vectors_on_the_device(fabe13, cuda):
+    """The same known-answer file as the CPU test, through the device entries (streaming kernel forced)."""
+    import os
+
+    import torch
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fabe13_own_kat_v1.npz"))
+    x = z["x"].view(np.float64)
+    xt = torch.from_numpy(x.copy()).to(cuda)
+    with np.errstate(all="ignore"):
+        xft = torch.from_numpy(x.astype(np.float32)).to(cuda)
+    fabe13.set_option("small_n", 0)
+    for core, tag in ((0, "poly"), (1, "psi")):
+        fabe13.set_option("core", core)
+        s, c, k = fabe13.sincos_k(xt)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(s.cpu().numpy()), z[f"{tag}/sin"]) and np.array_equal(bits(c.cpu().numpy()), z[f"{tag}/cos"])
+        assert np.array_equal(k.cpu().numpy(), z[f"{tag}/k"])
+        for fn, name in ((fabe13.tan_array, "tan"), (fabe13.cot_array, "cot"), (fabe13.sinc_array, "sinc")):
+            assert np.array_equal(bits(fn(xt).cpu().numpy()), z[f"{tag}/{name}"]), name
+        sf, cf = fabe13.sincosf(xft)
+        assert np.array_equal(sf.cpu().numpy().view(np.uint32), z[f"{tag}/sinf"])
+        assert np.array_equal(cf.cpu().numpy().view(np.uint32), z[f"{tag}/cosf"])
+
+
 def test_cuda_graph_capture_and_replay(fabe13, cuda, oracle):
     """Below hybrid_min_n a call is one kernel launch with no allocation, so it can be captured into a CUDA graph as it
     is; the hybrid sequence is captured with caller-provided scratch (fabe13_sincos_device_ws).  Replays recompute
