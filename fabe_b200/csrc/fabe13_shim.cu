@@ -11,6 +11,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include <atomic>
 #include <mutex>
 #include <thread>
@@ -56,6 +60,7 @@ struct Config {
     std::atomic<long long> host_devices{1};
     std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, 3/4 of the hardware threads)
     std::atomic<long long> zero_copy_max{(long long)1 << 24};
+    std::atomic<long long> stream_copy{1};  // staging copies of the pageable path with non-temporal stores
 };
 
 Config g_cfg;
@@ -87,6 +92,7 @@ const OptionDesc kOptions[] = {
     {"host_devices", "FABE13_CUDA_HOST_DEVICES", &Config::host_devices, 1, kMaxDevices},
     {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 0, kSlots},
     {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 30},
+    {"stream_copy", "FABE13_CUDA_STREAM_COPY", &Config::stream_copy, 0, 1},
 };
 
 void load_env() {
@@ -249,6 +255,48 @@ int run_device(const double* d_in, double* d_sin, double* d_cos, long long* d_k,
 // ---------------------------------------------------------------------------------------------------------------
 // host-pointer path: chunked pipeline through per-device slots
 // ---------------------------------------------------------------------------------------------------------------
+// The staging copies of the pageable path are bound by the host's memory bandwidth, and neither destination is read
+// by the CPU again soon (the staging buffer is read by the DMA engine, the caller's output array by the caller much
+// later): non-temporal stores skip the read-for-ownership of every destination line, a quarter of the traffic.
+// Option stream_copy = 0 restores memcpy.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void stream_copy_avx2(char* d, const char* s, size_t bytes) {  // d is 32-byte aligned
+    size_t i = 0;
+    for (; i + 128 <= bytes; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 64));
+        const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 96), e);
+    }
+    _mm_sfence();  // the DMA engine (or another thread) must see the data once this returns
+    if (i < bytes) memcpy(d + i, s + i, bytes - i);
+}
+#endif
+
+void staging_copy(void* dst, const void* src, size_t bytes) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2 && g_cfg.stream_copy.load(std::memory_order_relaxed) != 0 && bytes >= 4096) {
+        char* d = static_cast<char*>(dst);
+        const char* s = static_cast<const char*>(src);
+        const size_t lead = (32 - ((uintptr_t)d & 31)) & 31;  // stores must be 32-byte aligned; loads need not be
+        if (lead) {
+            memcpy(d, s, lead);
+            d += lead;
+            s += lead;
+            bytes -= lead;
+        }
+        stream_copy_avx2(d, s, bytes);
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+
 enum PtrKind { PTR_PAGEABLE, PTR_PINNED, PTR_DEVICE };
 
 PtrKind classify(const void* p) {
@@ -440,7 +488,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
         for (size_t i = (size_t)w; i < nchunks && rc_all.load() == 0; i += (size_t)workers) {
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
-            memcpy(sl.h_in, in + off, m * sizeof(double));
+            staging_copy(sl.h_in, in + off, m * sizeof(double));
             int rc = enqueue_chunk(*ds, sl, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core, op);
             if (rc == 0) {
                 cudaError_t e;
@@ -456,8 +504,8 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
                 rc_all.store(rc);
                 return;
             }
-            if (sin_out) memcpy(sin_out + off, sl.h_sin, m * sizeof(double));
-            if (cos_out) memcpy(cos_out + off, sl.h_cos, m * sizeof(double));
+            if (sin_out) staging_copy(sin_out + off, sl.h_sin, m * sizeof(double));
+            if (cos_out) staging_copy(cos_out + off, sl.h_cos, m * sizeof(double));
         }
     };
     if (workers <= 1) {
@@ -597,7 +645,7 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
         for (size_t i = (size_t)w; i < npieces && rc_all.load() == 0; i += (size_t)workers) {
             const size_t off = i * piece;
             const size_t m = n - off < piece ? n - off : piece;
-            memcpy(h_in, in + off, m * sizeof(float));
+            staging_copy(h_in, in + off, m * sizeof(float));
             int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, m, sl.stream);
             if (rc == 0) {
                 cudaError_t e = cudaStreamSynchronize(sl.stream);
@@ -607,8 +655,8 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
                 rc_all.store(rc);
                 return;
             }
-            memcpy(sin_out + off, h_s, m * sizeof(float));
-            memcpy(cos_out + off, h_c, m * sizeof(float));
+            staging_copy(sin_out + off, h_s, m * sizeof(float));
+            staging_copy(cos_out + off, h_c, m * sizeof(float));
         }
     };
     if (workers <= 1) {

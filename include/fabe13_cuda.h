@@ -106,7 +106,8 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
  * "hybrid_min_n", "local_min" / "dense_hint" (routing thresholds of the streaming kernel),
  * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
  * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
- * "zero_copy_max".  Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
+ * "zero_copy_max", "stream_copy" (staging copies of pageable arrays with non-temporal stores: 1 [default] / 0).
+ * Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);
 int fabe13_cuda_get_option(const char* key, long long* value);

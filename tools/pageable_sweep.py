@@ -20,15 +20,16 @@ s[:] = x
 t = time.perf_counter() - t0
 print(f"host memcpy, 1 thread: {8 * n / t / 1e9:.1f} GB/s read + the same written")
 fb.sincos(x[:1_000_000], out_sin=s[:1_000_000], out_cos=c[:1_000_000])
-for threads in (4, 8, 12, 16, 0):
+for threads, nt in ((8, 1), (8, 0), (0, 1), (0, 0), (16, 1), (16, 0), (8, 1), (8, 0), (0, 1), (0, 0)):
     fb.set_option("stage_threads", threads)
+    fb.set_option("stream_copy", nt)
     fb.sincos(x, out_sin=s, out_cos=c)
     ts = []
-    for _ in range(3):
+    for _ in range(4):
         t0 = time.perf_counter()
         fb.sincos(x, out_sin=s, out_cos=c)
         ts.append(time.perf_counter() - t0)
-    print(f"pageable, stage_threads={threads}: best {n / min(ts) / 1e9:.3f} Gelem/s  avg {n / (sum(ts) / 3) / 1e9:.3f}", flush=True)
+    print(f"pageable, stage_threads={threads}, stream_copy={nt}: best {n / min(ts) / 1e9:.3f} Gelem/s  avg {n / (sum(ts) / len(ts)) / 1e9:.3f}", flush=True)
 lib = fb._lib.load()
 t0 = time.perf_counter()
 for a in (x, s, c):
