@@ -443,7 +443,23 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
         if (rc >= 0) return rc;
     }
     size_t chunk = pick_chunk(n);
-    if (!pinned && chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;  // staged: 8 MB pieces, one per worker in flight
+    int stage_workers = 0;
+    if (!pinned) {
+        // staged: pieces of at most 8 MB, and small enough that every worker gets about three of them (a worker handles
+        // its pieces one after the other -- copy in, run, copy out -- so it is the other workers that overlap its stages)
+        stage_workers = (int)g_cfg.stage_threads.load();
+        if (stage_workers <= 0) {
+            // the staging copies are what bounds this path (measured: throughput still grows from 8 to 12 threads on
+            // a 16-thread host), so take most of the machine; the caller's own thread is worker 0
+            const unsigned hw = std::thread::hardware_concurrency();
+            const unsigned want = hw - hw / 4;
+            stage_workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
+        }
+        chunk = n / ((size_t)stage_workers * 3);
+        if (chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;
+        if (chunk < ((size_t)1 << 16)) chunk = (size_t)1 << 16;
+        chunk = (chunk + 3) & ~(size_t)3;
+    }
     const size_t nchunks = (n + chunk - 1) / chunk;
 
     if (pinned) {
@@ -468,14 +484,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
 
     // pageable memory: worker w owns slot w and the chunks i = w (mod workers); it copies the chunk into pinned
     // staging, runs it, waits, and copies the results out.  Workers overlap each other's stages.
-    int workers = (int)g_cfg.stage_threads.load();
-    if (workers <= 0) {
-        // the staging copies are what bounds this path (measured: throughput still grows linearly from 8 to 12
-        // threads on a 16-thread host), so take most of the machine; the caller's own thread is worker 0
-        const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned want = hw - hw / 4;
-        workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
-    }
+    int workers = stage_workers;
     if ((size_t)workers > nchunks) workers = (int)nchunks;
     if (int rc = ensure_slots(*ds, chunk, true, t, workers)) return rc;
     std::atomic<int> rc_all{0};
