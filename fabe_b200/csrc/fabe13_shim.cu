@@ -621,15 +621,19 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     // pageable memory: like the FP64 path, worker w owns slot w (its pinned staging buffers and its stream) and the
     // pieces i = w (mod workers): copy in, one kernel over the staging buffers in place (zero-copy over PCIe), copy out.
     // The staging copies bound this path (host memory bandwidth), hence the threads.
-    const size_t piece_doubles = (size_t)1 << 20;                 // staging buffers are sized in doubles: 8 MB each
-    const size_t piece = piece_doubles * sizeof(double) / sizeof(float);  // floats per piece
-    const size_t npieces = (n + piece - 1) / piece;
     int workers = (int)g_cfg.stage_threads.load();
     if (workers <= 0) {
         const unsigned hw = std::thread::hardware_concurrency();
         const unsigned want = hw - hw / 4;
         workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
     }
+    // pieces of at most 8 MB per staging buffer, small enough that every worker gets about three of them
+    size_t piece = n / ((size_t)workers * 3);                     // floats per piece
+    if (piece > ((size_t)1 << 21)) piece = (size_t)1 << 21;
+    if (piece < ((size_t)1 << 17)) piece = (size_t)1 << 17;
+    piece = (piece + 7) & ~(size_t)7;                             // keeps every piece's 32-byte phase
+    const size_t piece_doubles = (piece * sizeof(float) + sizeof(double) - 1) / sizeof(double);  // buffers are sized in doubles
+    const size_t npieces = (n + piece - 1) / piece;
     if ((size_t)workers > npieces) workers = (int)npieces;
     const LaunchTuning t = current_tuning();
     if (int rc = ensure_slots(*ds, piece_doubles, true, t, workers)) return rc;
