@@ -75,3 +75,14 @@ def test_narrower_vector_widths_exist_for_incongruent_pointers(sass):
     assert pick(sass, r"sincos_fused_kernelILi0ELi1E")
     for name, body in pick(sass, r"sincos_fused_kernelILi0ELi2ELi1ELb0ELi0E").items():
         assert count(body, r"LDG\.E\.NA\S*\.128") == 1 and count(body, r"STG\.E\.EF\S*\.128") == 2, name
+
+
+def test_fp32_and_derived_kernels_keep_vector_accesses_and_do_not_spill(sass):
+    for name, body in pick(sass, r"sincosf_kernelILi0E").items():
+        assert count(body, r"LDG\.E\.NA\S*\.256") == 1 and count(body, r"STG\.E\.EF\S*\.256") == 2, name   # eight floats per thread
+        assert count(body, r"\b(STL|LDL)\b") == 0, f"{name} spills registers"
+        assert count(body, r"\bF2F\.F32\.F64\b") >= 16                                                       # two roundings per element
+    for out in (3, 4, 5):  # tan, cot, sinc: one output vector, the checks-free division (MUFU.RCP64H) inline
+        (name, body), = pick(sass, rf"sincos_fused_kernelILi0ELi4ELi1ELb0ELi{out}ELb1E").items()
+        assert count(body, r"STG\.E\.EF\S*\.256") == 1 and count(body, r"\b(STL|LDL)\b") == 0, name
+        assert count(body, r"MUFU\.RCP64H") >= 4, name
