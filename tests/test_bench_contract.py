@@ -1,9 +1,11 @@
-"""bench.py's reference arm runs on the CPU, so its side of the output contract can be checked here: exactly one
-JSON line on stdout carrying the keys the driver reads."""
+"""bench.py's output contract: exactly one JSON line on stdout carrying the keys the driver reads.  The reference arm
+runs on the CPU and is checked everywhere; the CUDA arm is checked on the GPU box."""
 import json
 import os
 import subprocess
 import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -31,3 +33,29 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+
+@pytest.mark.gpu
+def test_cuda_arm_prints_one_json_line_with_the_contract_keys():
+    """The arm the driver runs on the B200: one JSON line with value / roofline / e2e / cpu_baseline / clocks /
+    gpu_launches (on a reduced element count so that the test takes seconds)."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "4", "--warmup", "3",
+                          "--elems", "80000000", "--e2e-elems", "20000000"], capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    j = json.loads(lines[0])
+    assert j["metric"] == "fp64_sincos_throughput" and j["unit"] == "Gelem/s" and j["dtype"] == "f64" and j["n_gpus"] == 1
+    assert j["steps"] == 4 and j["warmup"] == 3 and j["higher_is_better"] is True and j["vs_baseline"] is None
+    assert j["value"] > 50 and j["gpu_launches"] >= 4
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["algorithmic_bytes_per_launch"] == 24 * 80000000 and r["traffic"] is not None
+    e = j["e2e"]
+    assert e["value"] > 0.5 and e["h2d_bytes_per_step"] == 8 * 20000000 and e["d2h_bytes_per_step"] == 16 * 20000000
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] > 0 and j["cpu_baseline"]["cores"] >= 1
+    assert "sm_mhz" in j["clocks"] and "reasons" in j["clocks"] and "workload" in j["config"]
