@@ -143,3 +143,20 @@ def test_both_headers_are_plain_c99_and_cxx11(tmp_path):
     subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
     text = open(os.path.join(inc, "fabe13_cuda.h")).read() + open(os.path.join(inc, "fabe13.h")).read()
     assert "cuda_runtime" not in text and "torch" not in text
+
+
+def test_every_documented_option_exists_and_round_trips(fabe13):
+    """Every option named in include/fabe13_cuda.h's option list is known to the library (get and set work), and the
+    library knows no option the header does not name."""
+    hdr = open(os.path.join(ROOT, "include", "fabe13_cuda.h")).read()
+    block = hdr[hdr.index("/* Options:"):hdr.index("int fabe13_cuda_set_option")]
+    named = set(re.findall(r'"([a-z_0-9]+)"', block)) - {"launches", "device_count", "sm_count"}
+    assert len(named) >= 17, named
+    for key in sorted(named):
+        v = fabe13.get_option(key)          # KeyError = documented but unknown
+        fabe13.set_option(key, v)           # ValueError = its own current value rejected
+        assert fabe13.get_option(key) == v
+    src = open(os.path.join(ROOT, "fabe_b200", "csrc", "fabe13_shim.cu")).read()
+    table = src[src.index("const OptionDesc kOptions[]"):src.index("void load_env()")]
+    implemented = set(re.findall(r'\{"([a-z_0-9]+)", "FABE13_CUDA_', table))
+    assert implemented == named, (implemented ^ named)
