@@ -212,6 +212,49 @@ struct FusedShared {
     uint16_t off[kWarps][kWarpElems];             // their element offsets inside the tile
 };
 
+// what a tiny (special = false) or NaN/Inf (special = true) argument returns: reference fabe13.c:597-600
+__device__ __noinline__ ulonglong2 override_values(uint64_t x_bits, bool special) {
+    ulonglong2 o;
+    o.x = special ? FABE13_QNAN_BITS : x_bits;
+    o.y = special ? FABE13_QNAN_BITS : FABE13_ONE_BITS;
+    return o;
+}
+
+// fabe13_sincos_one for a warp running in lockstep (all 32 lanes call it together): same reduction, core and rotation;
+// the tiny / NaN / Inf overrides -- selects that fabe13_sincos_one applies to every element -- are entered only if
+// a warp vote finds a lane that needs one.  Same bits as fabe13_sincos_one for every input.
+template <int CORE>
+__device__ __forceinline__ void sincos_one_lockstep(uint64_t x_bits, const uint32_t* ph_stream, uint64_t* s_bits,
+                                                    uint64_t* c_bits, int64_t* k_out) {
+    const uint32_t ahi = fabe13_abs_hi(x_bits);
+    double r;
+    uint32_t q;
+    if (fabe13_is_huge(ahi)) {
+        r = fabe13_payne_hanek(x_bits, ph_stream, &q);
+        *k_out = (int64_t)q;
+    } else {
+        const double x = fabe13_from_bits(x_bits);
+        double biased;
+        const double kd = fabe13_quadrant_index(x, &biased);
+        r = fabe13_cody_waite(x, kd);
+        q = fabe13_q_from_biased(biased);
+        *k_out = fabe13_is_special(ahi) ? 0 : fabe13_k_from_biased(biased);
+    }
+    double sr, cr;
+    fabe13_core<CORE>(r, &sr, &cr);
+    fabe13_rotate(sr, cr, q, s_bits, c_bits);
+    const bool special = fabe13_is_special(ahi);
+    const bool override_ = special || fabe13_is_tiny(ahi);
+    if (__any_sync(0xFFFFFFFFu, override_)) {
+        // (a call, because ptxas turns a short block into predicated selects again, vote or no vote)
+        const ulonglong2 o = override_values(x_bits, special);
+        if (override_) {
+            *s_bits = o.x;
+            *c_bits = o.y;
+        }
+    }
+}
+
 // The rounds of the dense-warp route (see fused_tile).  Not inlined: its register allocation must not leak into the
 // streaming path (inlined, ptxas spilled the fast path's live vectors around it).  The caller has parked the lane's
 // arguments in sh.x[warp][r*32 + lane], r = u*VEC + j, and picks the results up from sh.x (sines) and sh.c (cosines)
@@ -229,7 +272,7 @@ __device__ __noinline__ void dense_rounds(long long* k_out, uint32_t head, uint3
         uint64_t s1, c1;
         int64_t k;
         const uint64_t xr = sh.x[warp][r * 32 + lane];
-        fabe13_sincos_one<CORE>(xr, sh.table[warp], &s1, &c1, &k);
+        sincos_one_lockstep<CORE>(xr, sh.table[warp], &s1, &c1, &k);
         if (out_derived(OUT)) s1 = fabe13_derived<OUT>(xr, s1, c1);
         sh.x[warp][r * 32 + lane] = s1;
         if (out_second(OUT)) sh.c[warp][r * 32 + lane] = c1;

@@ -166,7 +166,7 @@ struct DeviceState {
     bool ready = false;
     DeviceInfo info{};
     cudaMemPool_t pool = nullptr;  // stream-ordered scratch for the device-pointer entry points
-    char name[256] = {0};
+    char name[320] = {0};
     // host path
     std::mutex pipe_mu;
     cudaStream_t small_stream = nullptr;  // small host calls: one kernel reading/writing pinned host memory directly
