@@ -86,3 +86,25 @@ def test_fp32_and_derived_kernels_keep_vector_accesses_and_do_not_spill(sass):
         (name, body), = pick(sass, rf"sincos_fused_kernelILi0ELi4ELi1ELb0ELi{out}ELb1E").items()
         assert count(body, r"STG\.E\.EF\S*\.256") == 1 and count(body, r"\b(STL|LDL)\b") == 0, name
         assert count(body, r"MUFU\.RCP64H") >= 4, name
+
+
+def test_payne_hanek_product_has_no_accumulator_moves(sass):
+    """The 53 x 192-bit product of the Payne-Hanek reduction (csrc/fabe13_core.h) is nine independent IMAD.WIDE with a
+    zero addend plus carry chains.  Its first form (a running 64-bit accumulator per chain) needed two register moves per
+    step to build the next addend pair, which showed up as `VIADD Rx, Ry, URz` with a zeroed uniform register and cost
+    7 % on the extreme-range workload (profiles/r01_ab_ph_multiply.txt).  Checked on the dense-rounds routine of the
+    default hot kernel: the code after its CALL target."""
+    (name, body), = pick(sass, r"sincos_fused_kernelILi0ELi4ELi1ELb0ELi0ELb1E").items()
+    text = [re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line) for line in body]
+    target = next(re.search(r"CALL\.REL\.NOINC (0x[0-9a-f]+)", line).group(1) for line in text if "CALL.REL.NOINC" in line)
+    start = next(i for i, line in enumerate(text) if f"/*{int(target, 16):04x}*/" in line)
+    dense = text[start:]
+    loop_end = max(i for i, line in enumerate(dense) if re.search(r"\bBRA\.U\b", line))
+    rounds = dense[:loop_end + 1]
+    wide = [line for line in rounds if "IMAD.WIDE.U32" in line]
+    assert 7 <= len(wide) <= 9, wide                               # (two of the nine may be emitted as IMAD.HI / IMAD)
+    assert all(re.search(r", RZ ;", line) for line in wide), wide   # independent products: no 64-bit addend
+    assert count(rounds, r"VIADD R\d+, R\d+, UR\d+ ;") <= 1, name   # (the one allowed: the round's shared-memory address)
+    assert count(rounds, r"\bVOTE\.ANY\b") == 1, name               # the overrides sit behind a warp vote ...
+    assert count(rounds, r"CALL\.REL") == 1, name                    # ... and a real branch (around a call)
+    assert len(rounds) <= 175, len(rounds)                          # 196 before the rewrite
