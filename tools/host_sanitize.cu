@@ -1,0 +1,121 @@
+// host_sanitize.cu -- the host side of libfabe13 (scalar API, the host instantiation of the per-element core, option
+// table, shard arithmetic, the oracle-independent debug hooks) under AddressSanitizer + UndefinedBehaviorSanitizer.
+// No GPU needed: nothing here launches a kernel.  Stands in for SURVEY section 5's "host ASan/UBSan build of shim".
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -cudart static \
+//        -Xcompiler -fsanitize=address,undefined,-fno-sanitize-recover=all,-ffp-contract=off,-mfma \
+//        -o tools/host_sanitize tools/host_sanitize.cu fabe_b200/csrc/fabe13_kernels.cu fabe_b200/csrc/fabe13_shim.cu -lpthread
+//   tools/host_sanitize        (exit code 0 and "host_sanitize: ok" = clean)
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../include/fabe13.h"
+#include "../include/fabe13_cuda.h"
+
+static uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static double from_bits(uint64_t u) {
+    double x;
+    memcpy(&x, &u, sizeof x);
+    return x;
+}
+
+int main() {
+    std::vector<double> in;
+    // every exponent, with all-zero, all-one and alternating mantissas, both signs: walks the whole 2/pi table
+    for (uint64_t e = 0; e < 2048; ++e)
+        for (uint64_t m : {0x0ull, 0xFFFFFFFFFFFFFull, 0xAAAAAAAAAAAAAull, 0x5555555555555ull, 0x8000000000000ull, 0x1ull})
+            for (uint64_t s = 0; s < 2; ++s) in.push_back(from_bits((s << 63) | (e << 52) | m));
+    // multiples of pi/2 and their neighbours; the double closest to a multiple of pi/2
+    for (int k = -2000; k <= 2000; ++k) {
+        const double x = k * 1.5707963267948966;
+        in.push_back(x);
+        in.push_back(nextafter(x, INFINITY));
+        in.push_back(nextafter(x, -INFINITY));
+    }
+    in.push_back(ldexp(6381956970095103.0, 797));
+    in.push_back(1e22);
+    in.push_back(0x1p45);
+    in.push_back(nextafter(0x1p45, 0.0));
+    uint64_t seed = 0xFABE13;
+    for (int i = 0; i < 2000000; ++i) in.push_back(from_bits(splitmix64(seed)));  // random bit patterns
+    const size_t n = in.size();
+    // exactly-sized heap arrays: ASan sees any access past either end
+    std::vector<double> s(n), c(n), d(n);
+    std::vector<long long> k(n);
+    double acc = 0;
+    for (int core = 0; core < 2; ++core) {
+        fabe13_debug_host_core(in.data(), s.data(), c.data(), k.data(), n, core);
+        for (size_t i = 0; i < n; ++i)
+            if (s[i] == s[i]) acc += s[i] + c[i];
+        for (int op = 3; op <= 5; ++op) {
+            fabe13_debug_host_derived(in.data(), d.data(), n, op, core);
+            for (size_t i = 0; i < n; i += 97)
+                if (d[i] == d[i] && fabs(d[i]) < 1e300) acc += d[i];
+        }
+    }
+    std::vector<float> fin(n), fs(n), fc(n);
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t b = splitmix64(seed);
+        uint32_t w = (uint32_t)b;
+        memcpy(&fin[i], &w, 4);
+    }
+    for (int core = 0; core < 2; ++core) fabe13_debug_host_sincosf(fin.data(), fs.data(), fc.data(), n, core);
+    for (size_t i = 0; i < n; i += 1000) {  // scalar API (the array core, one element)
+        const double x = in[i];
+        acc += fabe13_sin(x) == fabe13_sin(x) ? fabe13_cos(x) : 0;
+        const double t = fabe13_tan(x), ct = fabe13_cot(x), sc = fabe13_sinc(x);
+        if (t == t && fabs(t) < 1e300) acc += t;
+        if (ct == ct && fabs(ct) < 1e300) acc += ct;
+        if (sc == sc) acc += sc;
+        (void)fabe13_atan(x);
+        (void)fabe13_asin(x);
+        (void)fabe13_acos(x);
+    }
+    // no-ops and argument checks that must not touch memory
+    fabe13_sincos(nullptr, nullptr, nullptr, 0);
+    fabe13_sincos(nullptr, nullptr, nullptr, -5);
+    (void)fabe13_sincos_host(nullptr, nullptr, nullptr, 0);
+    (void)fabe13_sincosf_host(nullptr, nullptr, nullptr, 0);
+    (void)fabe13_get_active_simd_width();
+    // shard arithmetic
+    for (size_t total : {(size_t)0, (size_t)1, (size_t)3, (size_t)1000003, (size_t)1000000000, (size_t)1 << 40})
+        for (int world : {1, 2, 3, 8, 64}) {
+            size_t prev = 0;
+            for (int r = 0; r < world; ++r) {
+                size_t b, e;
+                fabe13_shard_bounds(total, world, r, &b, &e);
+                if (b != prev || e < b || e > total) {
+                    fprintf(stderr, "shard bounds broken: n=%zu world=%d rank=%d [%zu,%zu)\n", total, world, r, b, e);
+                    return 1;
+                }
+                prev = e;
+            }
+            if (prev != total) return 1;
+        }
+    // option table: every documented key, out-of-range values, unknown and empty keys
+    const char* keys[] = {"core", "unroll", "blocks_per_sm", "tiles_per_block", "small_n", "worklist", "hybrid_min_n", "local_min",
+                          "dense_hint", "worklist_shift", "second_pass_blocks_per_sm", "pdl", "chunk_elems", "host_devices",
+                          "stage_threads", "zero_copy_max", "stream_copy", "launches", "no_such_option", ""};
+    for (const char* key : keys) {
+        long long v = 0;
+        const int rc = fabe13_cuda_get_option(key, &v);
+        if (rc == 0) (void)fabe13_cuda_set_option(key, v);
+        (void)fabe13_cuda_set_option(key, -1);
+        (void)fabe13_cuda_set_option(key, (long long)1 << 62);
+    }
+    (void)fabe13_sincos_workspace_bytes(0);
+    (void)fabe13_sincos_workspace_bytes((size_t)1 << 30);
+    printf("host_sanitize: ok (%zu doubles x 2 cores, checksum %.17g)\n", n, acc);
+    return 0;
+}
