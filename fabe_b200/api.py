@@ -25,6 +25,24 @@ def _check_f64(x, name):
             raise TypeError(f"{name} must be a C-contiguous float64 array")
 
 
+def _check_out(out, x, name, dtype_name="float64"):
+    """A caller-provided output must be the same kind of object as x, with x's element count, dtype and device:
+    the library writes numel(x) elements through the raw pointer and cannot check any of this itself."""
+    if _is_torch(out) != _is_torch(x):
+        raise TypeError(f"{name} must be a {'torch tensor' if _is_torch(x) else 'numpy array'} like x")
+    if _is_torch(x):
+        import torch
+
+        if out.dtype != getattr(torch, dtype_name) or not out.is_contiguous():
+            raise TypeError(f"{name} must be a contiguous {dtype_name} tensor")
+        if out.device != x.device:
+            raise ValueError(f"{name} is on {out.device}, x on {x.device}")
+    elif out.dtype != np.dtype(dtype_name) or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+        raise TypeError(f"{name} must be a writeable C-contiguous {dtype_name} array")
+    if _numel(out) != _numel(x):
+        raise ValueError(f"{name} has {_numel(out)} elements, x has {_numel(x)}")
+
+
 def _ptr(x):
     return x.data_ptr() if _is_torch(x) else x.ctypes.data
 
@@ -46,8 +64,8 @@ def sincos(x, out_sin=None, out_cos=None, stream=None):
 
         s = torch.empty_like(x) if out_sin is None else out_sin
         c = torch.empty_like(x) if out_cos is None else out_cos
-        _check_f64(s, "out_sin")
-        _check_f64(c, "out_cos")
+        _check_out(s, x, "out_sin")
+        _check_out(c, x, "out_cos")
         if x.is_cuda:
             with torch.cuda.device(x.device):
                 st = torch.cuda.current_stream().cuda_stream if stream is None else stream
@@ -59,8 +77,8 @@ def sincos(x, out_sin=None, out_cos=None, stream=None):
         return s, c
     s = np.empty_like(x) if out_sin is None else out_sin
     c = np.empty_like(x) if out_cos is None else out_cos
-    _check_f64(s, "out_sin")
-    _check_f64(c, "out_cos")
+    _check_out(s, x, "out_sin")
+    _check_out(c, x, "out_cos")
     rc = lib.fabe13_sincos_host(x.ctypes.data, s.ctypes.data, c.ctypes.data, x.size)
     _lib.check(rc, "fabe13_sincos_host")
     return s, c
@@ -73,7 +91,7 @@ def _single(x, out, dev_fn, host_fn, what):
         import torch
 
         o = torch.empty_like(x) if out is None else out
-        _check_f64(o, "out")
+        _check_out(o, x, "out")
         if x.is_cuda:
             with torch.cuda.device(x.device):
                 rc = getattr(lib, dev_fn)(x.data_ptr(), o.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream)
@@ -82,7 +100,7 @@ def _single(x, out, dev_fn, host_fn, what):
         _lib.check(rc, what)
         return o
     o = np.empty_like(x) if out is None else out
-    _check_f64(o, "out")
+    _check_out(o, x, "out")
     _lib.check(getattr(lib, host_fn)(x.ctypes.data, o.ctypes.data, x.size), what)
     return o
 
@@ -126,6 +144,8 @@ def sincosf(x, out_sin=None, out_cos=None):
             raise TypeError("x must be a contiguous float32 tensor")
         s = torch.empty_like(x) if out_sin is None else out_sin
         c = torch.empty_like(x) if out_cos is None else out_cos
+        _check_out(s, x, "out_sin", "float32")
+        _check_out(c, x, "out_cos", "float32")
         if x.is_cuda:
             with torch.cuda.device(x.device):
                 rc = lib.fabe13_sincosf_device(x.data_ptr(), s.data_ptr(), c.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream)
@@ -137,6 +157,8 @@ def sincosf(x, out_sin=None, out_cos=None):
         raise TypeError("x must be a C-contiguous float32 array")
     s = np.empty_like(x) if out_sin is None else out_sin
     c = np.empty_like(x) if out_cos is None else out_cos
+    _check_out(s, x, "out_sin", "float32")
+    _check_out(c, x, "out_cos", "float32")
     _lib.check(lib.fabe13_sincosf_host(x.ctypes.data, s.ctypes.data, c.ctypes.data, x.size), "fabe13_sincosf_host")
     return s, c
 
@@ -172,6 +194,11 @@ def sincos_k(x):
 def sincos_legacy(x, s, c):
     """The reference's own entry point, void fabe13_sincos(in, sin_out, cos_out, int n), on host or device memory."""
     lib = _lib.load()
+    _check_f64(x, "x")
+    _check_out(s, x, "s")
+    _check_out(c, x, "c")
+    if _numel(x) > 0x7FFFFFFF:
+        raise ValueError("fabe13_sincos takes an int n (reference fabe13.h:49): at most 2^31 - 1 elements")
     lib.fabe13_cuda_clear_error()
     lib.fabe13_sincos(_ptr(x), _ptr(s), _ptr(c), _numel(x))
     _lib.check(lib.fabe13_cuda_last_error(), "fabe13_sincos")

@@ -160,3 +160,44 @@ def test_every_documented_option_exists_and_round_trips(fabe13):
     table = src[src.index("const OptionDesc kOptions[]"):src.index("void load_env()")]
     implemented = set(re.findall(r'\{"([a-z_0-9]+)", "FABE13_CUDA_', table))
     assert implemented == named, (implemented ^ named)
+
+
+def test_python_layer_rejects_outputs_the_library_cannot_check(fabe13):
+    """The C entry points write numel(x) elements through raw pointers; the Python layer therefore refuses outputs of
+    the wrong size, dtype, kind or device, and read-only arrays, before anything reaches the library."""
+    import torch
+    from fabe_b200 import api
+
+    x = np.zeros(16)
+    for bad, exc in ((np.zeros(8), ValueError), (np.zeros(16, dtype=np.float32), TypeError),
+                     (np.zeros(32)[::2], TypeError), (torch.zeros(16, dtype=torch.float64), TypeError)):
+        with pytest.raises(exc):
+            fabe13.sincos(x, out_sin=bad)
+        with pytest.raises(exc):
+            fabe13.sincos(x, out_cos=bad)
+        with pytest.raises(exc):
+            fabe13.tan_array(x, out=bad)
+        with pytest.raises(exc):
+            fabe13.sincos_legacy(x, bad, np.zeros(16))
+    ro = np.zeros(16)
+    ro.flags.writeable = False
+    with pytest.raises(TypeError):
+        fabe13.sin_array(x, out=ro)
+    xf = np.zeros(16, dtype=np.float32)
+    with pytest.raises(ValueError):
+        fabe13.sincosf(xf, out_sin=np.zeros(4, dtype=np.float32))
+    with pytest.raises(TypeError):
+        fabe13.sincosf(xf, out_cos=np.zeros(16))
+    xt = torch.zeros(16, dtype=torch.float64)
+    with pytest.raises(ValueError):
+        fabe13.sincos(xt, out_sin=torch.zeros(15, dtype=torch.float64))
+    with pytest.raises(TypeError):
+        fabe13.sincos(xt, out_sin=np.zeros(16))
+    # what the tests and bench.py pass is accepted: same-size slices, in-place, views of one buffer
+    buf = np.zeros(40)
+    api._check_out(buf[3:19], x, "out")
+    api._check_out(x, x, "out")
+    tb = torch.zeros(40, dtype=torch.float64)
+    api._check_out(tb[5:21], xt, "out")
+    api._check_out(xt, xt, "out")
+    api._check_out(torch.zeros(16, dtype=torch.float32), torch.zeros(16, dtype=torch.float32), "out", "float32")
