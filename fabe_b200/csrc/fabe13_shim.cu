@@ -469,8 +469,12 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
             if (int rc = enqueue_chunk(*ds, ds->slots[i % kPipeSlots], in + off, sin_out ? sin_out + off : nullptr,
-                                       cos_out ? cos_out + off : nullptr, m, t, core, op))
+                                       cos_out ? cos_out + off : nullptr, m, t, core, op)) {
+                // earlier chunks are still copying into the caller's arrays: do not hand the arrays back mid-flight
+                for (int j = 0; j < kPipeSlots; ++j) (void)cudaStreamSynchronize(ds->slots[j].stream);
+                (void)cudaGetLastError();
                 return rc;
+            }
         }
         if (n >= ((size_t)1 << 22)) {
             // large transfers: sleep on blocking events rather than spin (the wait is milliseconds long)
