@@ -889,6 +889,7 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
 }
 
 int fabe13_cuda_set_option(const char* key, long long value) {
+    if (!key) return -1;
     load_env();
     for (const OptionDesc& o : kOptions) {
         if (strcmp(o.key, key) == 0) {
@@ -901,6 +902,7 @@ int fabe13_cuda_set_option(const char* key, long long value) {
 }
 
 int fabe13_cuda_get_option(const char* key, long long* value) {
+    if (!key || !value) return -1;
     load_env();
     for (const OptionDesc& o : kOptions) {
         if (strcmp(o.key, key) == 0) {

@@ -114,6 +114,14 @@ int main() {
         (void)fabe13_cuda_set_option(key, -1);
         (void)fabe13_cuda_set_option(key, (long long)1 << 62);
     }
+    {
+        long long v = 0;
+        if (fabe13_cuda_set_option(nullptr, 1) != -1 || fabe13_cuda_get_option(nullptr, &v) != -1 ||
+            fabe13_cuda_get_option("core", nullptr) != -1) {
+            fprintf(stderr, "null option arguments must be refused with -1\n");
+            return 1;
+        }
+    }
     (void)fabe13_sincos_workspace_bytes(0);
     (void)fabe13_sincos_workspace_bytes((size_t)1 << 30);
     printf("host_sanitize: ok (%zu doubles x 2 cores, checksum %.17g)\n", n, acc);
