@@ -267,11 +267,14 @@ def test_hypothesis_edge_biased_floats(fabe13, oracle):
     run()
 
 
-def test_host_side_is_clean_under_asan_and_ubsan(tmp_path):
+@pytest.mark.parametrize("flavour", ["address+undefined", "thread"])
+def test_host_side_is_clean_under_sanitizers(tmp_path, flavour):
     """The host side of the library -- scalar API, the host instantiation of the per-element core over every exponent,
-    2e6 random bit patterns, the FP32 and derived variants, option table, shard arithmetic -- built with
-    -fsanitize=address,undefined and -fno-sanitize-recover (tools/host_sanitize.cu).  No GPU needed."""
+    2e6 random bit patterns, the FP32 and derived variants, option table, shard arithmetic, and eight threads calling
+    the scalar API and the option table at once -- built with -fsanitize=address,undefined (-fno-sanitize-recover) and
+    with -fsanitize=thread (tools/host_sanitize.cu).  No GPU needed."""
     import os
+    import re
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -279,16 +282,21 @@ def test_host_side_is_clean_under_asan_and_ubsan(tmp_path):
         pytest.skip("nvcc not found")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "host_sanitize")
-    san = ["-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize-recover=all", "-ffp-contract=off", "-mfma"]
+    if flavour == "thread":
+        san = ["-fsanitize=thread"]
+    else:
+        san = ["-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize-recover=all"]
+    san += ["-ffp-contract=off", "-mfma"]
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-g", "-std=c++17", "-cudart", "static"]
     for f in san:
         cmd += ["-Xcompiler", f]
     cmd += ["-o", exe] + [os.path.join(root, p) for p in ("tools/host_sanitize.cu", "fabe_b200/csrc/fabe13_kernels.cu",
                                                            "fabe_b200/csrc/fabe13_shim.cu")] + ["-lpthread"]
     build = subprocess.run(cmd, capture_output=True, text=True)
-    if build.returncode != 0 and "asan" in (build.stderr + build.stdout).lower():
+    if build.returncode != 0 and re.search(r"lib(a|t|ub)san", build.stderr + build.stdout):
         pytest.skip("sanitizer runtime not installed")
     assert build.returncode == 0, build.stderr[-2000:]
-    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
     assert run.returncode == 0, (run.stdout + run.stderr)[-4000:]
-    assert "host_sanitize: ok" in run.stdout
+    assert "host_sanitize: ok" in run.stdout and "WARNING: ThreadSanitizer" not in run.stderr

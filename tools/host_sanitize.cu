@@ -6,12 +6,14 @@
 //        -Xcompiler -fsanitize=address,undefined,-fno-sanitize-recover=all,-ffp-contract=off,-mfma \
 //        -o tools/host_sanitize tools/host_sanitize.cu fabe_b200/csrc/fabe13_kernels.cu fabe_b200/csrc/fabe13_shim.cu -lpthread
 //   tools/host_sanitize        (exit code 0 and "host_sanitize: ok" = clean)
+// and the same with -Xcompiler -fsanitize=thread instead of address,undefined for the threaded section at the end.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "../include/fabe13.h"
@@ -121,6 +123,30 @@ int main() {
             fprintf(stderr, "null option arguments must be refused with -1\n");
             return 1;
         }
+    }
+    // the entry points are re-entrant (reference: globals written once at load, fabe13.c:209-214): scalar calls, option
+    // reads and writes and the host instantiation from eight threads at once (the interesting build for this part is
+    // -fsanitize=thread)
+    {
+        std::vector<std::thread> th;
+        std::vector<double> sums(8, 0.0);
+        for (int w = 0; w < 8; ++w)
+            th.emplace_back([&, w] {
+                std::vector<double> ls(4096), lc(4096);
+                for (int rep = 0; rep < 20; ++rep) {
+                    fabe13_debug_host_core(in.data() + (size_t)w * 4096, ls.data(), lc.data(), nullptr, 4096, rep & 1);
+                    (void)fabe13_cuda_set_option("core", rep & 1);
+                    long long v = 0;
+                    (void)fabe13_cuda_get_option("core", &v);
+                    for (int i = 0; i < 256; ++i) {
+                        const double y = fabe13_sin(0.001 * i + w);
+                        if (y == y) sums[(size_t)w] += y + fabe13_cos(1e300 * (i + 1)) + fabe13_tan(0.5 + i);
+                    }
+                }
+            });
+        for (std::thread& t : th) t.join();
+        for (double v : sums) acc += v;
+        (void)fabe13_cuda_set_option("core", 0);
     }
     (void)fabe13_sincos_workspace_bytes(0);
     (void)fabe13_sincos_workspace_bytes((size_t)1 << 30);
