@@ -13,7 +13,7 @@ _lib = None
 
 
 class Fabe13Error(RuntimeError):
-    """A CUDA error reported by libfabe13.so (there is no CPU fallback to hide it)."""
+    """A CUDA error reported by libfabe13.so (every int entry point returns it; nothing hides it)."""
 
 
 def signatures():
@@ -64,6 +64,9 @@ def signatures():
         "fabe13_debug_host_core": (None, [_vp, _vp, _vp, _vp, c.c_size_t, c.c_int]),
         "fabe13_debug_host_sincosf": (None, [_vp, _vp, _vp, c.c_size_t, c.c_int]),
         "fabe13_debug_host_derived": (None, [_vp, _vp, c.c_size_t, c.c_int, c.c_int]),
+        "fabe13_debug_host_array": (None, [_vp, _vp, _vp, c.c_size_t, c.c_int, c.c_int, c.c_int]),
+        "fabe13_cuda_trim": (c.c_int, []),
+        "fabe13_cuda_shutdown": (c.c_int, []),
         "fabe13_debug_fill_uniform_device": (c.c_int, [_vp, c.c_size_t, c.c_uint64, c.c_uint64, c.c_double, c.c_double, _vp]),
         "fabe13_debug_fill_loguniform_device": (c.c_int, [_vp, c.c_size_t, c.c_uint64, c.c_uint64, _vp]),
     }

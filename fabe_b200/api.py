@@ -254,29 +254,56 @@ def shard_bounds(n, world, rank):
     return b.value, e.value
 
 
-class PinnedArray:
-    """A float64 numpy array in page-locked host memory from fabe13_cuda_host_alloc (fast host path)."""
+class _PinnedBlock:
+    """Owner of one fabe13_cuda_host_alloc block; exposes the buffer protocol so numpy views keep it alive."""
 
-    def __init__(self, n):
-        lib = _lib.load()
+    def __init__(self, lib, nbytes):
         self._lib = lib
-        self._p = lib.fabe13_cuda_host_alloc(max(int(n), 1) * 8)
+        self._p = lib.fabe13_cuda_host_alloc(max(int(nbytes), 8))
         if not self._p:
-            raise MemoryError(f"fabe13_cuda_host_alloc({n * 8}) failed")
-        buf = (ctypes.c_double * int(n)).from_address(self._p)
-        self.array = np.frombuffer(buf, dtype=np.float64, count=int(n))
+            raise MemoryError(f"fabe13_cuda_host_alloc({nbytes}) failed")
+        self.buf = (ctypes.c_char * int(nbytes)).from_address(self._p)
 
-    def free(self):
+    def release(self):
         if self._p:
-            self.array = None
             self._lib.fabe13_cuda_host_free(self._p)
             self._p = None
 
     def __del__(self):
         try:
-            self.free()
+            self.release()
         except Exception:
             pass
+
+
+class _PinnedNdarray(np.ndarray):
+    """ndarray whose views carry a reference to the pinned block they look into (through .base chains and this
+    attribute), so the page-locked memory is freed only when the last view is gone."""
+
+    _fabe13_owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._fabe13_owner = getattr(obj, "_fabe13_owner", None)
+
+
+class PinnedArray:
+    """A float64 numpy array in page-locked host memory from fabe13_cuda_host_alloc (fast host path).
+
+    `.array` (and every view or slice of it) keeps the block alive: `a = PinnedArray(n).array` is safe, the memory is
+    returned when the last such array is garbage-collected.  free() drops this wrapper's own reference only."""
+
+    def __init__(self, n):
+        lib = _lib.load()
+        n = int(n)
+        block = _PinnedBlock(lib, n * 8)
+        arr = np.frombuffer(block.buf, dtype=np.float64, count=n).view(_PinnedNdarray)
+        arr._fabe13_owner = block
+        self.array = arr
+
+    def free(self):
+        """Drop this wrapper's reference; the block is freed once no view of .array is left."""
+        self.array = None
 
 
 def fill_uniform_device(t, seed, lo, hi, first_index=0):

@@ -4,6 +4,7 @@ The .so lands in fabe_b200/lib/ so that it travels with the repository snapshot 
 JIT-compiled at import time.  `python -m fabe_b200.build` rebuilds it.
 """
 import os
+import platform
 import shutil
 import subprocess
 import sys
@@ -13,8 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libfabe13.so")
 
-SOURCES = ["fabe13_kernels.cu", "fabe13_shim.cu"]
-HEADERS = ["fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h"]
+SOURCES = ["fabe13_kernels.cu", "fabe13_shim.cu", "fabe13_hostcore.cpp"]
+HEADERS = ["fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h", "fabe13_hostcore.h"]
 
 
 def _nvcc():
@@ -49,8 +50,10 @@ def build_library(force=False, verbose=False, out=None):
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-lineinfo", "-std=c++17",
         "-shared", "-cudart", "static",
-        # host side: keep * and + as separate roundings (the host scalar API must match the device bit for bit)
-        "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-mfma,-fvisibility=hidden",
+        # host side: keep * and + as separate roundings (the host core must match the device bit for bit); -O3 so that
+        # the host array loop (fabe13_hostcore.cpp) is vectorised; -mfma only where the flag exists (x86: fma() must
+        # inline to the instruction; aarch64 has fused multiply-add in its base ISA and gcc rejects the flag there)
+        "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-fvisibility=hidden" + (",-mfma" if platform.machine() in ("x86_64", "AMD64") else ""),
         "-Xptxas", "-v" if verbose else "-O3",
     ] + [f"-D{d}" for d in os.environ.get("FABE13_BUILD_DEFINES", "").split() if d] + [
         "-o", target,

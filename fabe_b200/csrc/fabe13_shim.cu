@@ -3,10 +3,15 @@
 //
 // Mirrors the reference's dispatcher layer (fabe13/fabe13.c:132-135 global state, :186-219 initialisation and
 // getters, :222-259 fabe13_sincos, :262-269 scalar API) with the ISA switch replaced by: device pointers -> one
-// stream-ordered launch sequence; host pointers -> chunked H2D | kernel | D2H pipeline.  There is no CPU fallback
-// for the array path: a CUDA failure is recorded, reported on stderr and returned.
+// stream-ordered launch sequence; host pointers -> chunked H2D | kernel | D2H pipeline, except that host-pointer calls
+// below option "min_n" run the HOST INSTANTIATION of the same per-element core (fabe13_hostcore.cpp; same bits as the
+// device) -- the counterpart of the reference's n < 32 scalar route (fabe13/fabe13.c:226-229): a kernel launch costs
+// ~13 us, the host core ~2 ns per element.  A CUDA failure is recorded (sticky, per thread), reported on stderr and
+// returned by every int entry point; the void fabe13_sincos, whose ABI has no error channel (fabe13/fabe13.h:51-56),
+// then fills its outputs with the host core so that callers never read unwritten memory.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,6 +22,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <new>
+#include <shared_mutex>
 #include <thread>
 #include <vector>
 
@@ -25,6 +32,7 @@
 #include "../../include/fabe13_cuda.h"
 #pragma GCC visibility pop
 #include "fabe13_core.h"
+#include "fabe13_hostcore.h"
 #include "fabe13_internal.h"
 
 namespace {
@@ -37,8 +45,7 @@ constexpr int kSlots = 16;                                 // max staging worker
 constexpr int kPipeSlots = 8;                              // pipeline depth for pinned callers (copy engines only)
 constexpr size_t kLaunchMaxElems = (size_t)1 << 30;        // per launch sequence; keeps 32-bit indices and alignment
 constexpr size_t kZeroCopyPageableMax = 32768;             // pageable callers: bounce through one small pinned block
-
-const uint32_t h_ph_stream[FABE13_PH_STREAM_WORDS] = FABE13_PH_STREAM;
+constexpr unsigned long long kPoolKeepBytes = 256ull << 20;  // scratch the stream-ordered pool keeps between calls
 
 // ---------------------------------------------------------------------------------------------------------------
 // configuration (reference: compile-time constants fabe13/fabe13.c:71-73; here run-time options)
@@ -61,12 +68,18 @@ struct Config {
     std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, 3/4 of the hardware threads)
     std::atomic<long long> zero_copy_max{(long long)1 << 24};
     std::atomic<long long> stream_copy{1};  // staging copies of the pageable path with non-temporal stores
+    std::atomic<long long> min_n{8192};     // host-pointer calls below this many elements stay on the host core
+    std::atomic<long long> fallback{1};     // void fabe13_sincos(): on a CUDA failure fill the outputs on the host core
+    std::atomic<long long> host_threads{0}; // threads of that fallback (0 = auto: the hardware threads, at most 16)
 };
 
 Config g_cfg;
 std::once_flag g_cfg_once;
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_last_error{0};
+std::atomic<unsigned long long> g_host_core_calls{0};  // array calls served by the host core (small n)
+std::atomic<unsigned long long> g_fallbacks{0};        // fabe13_sincos calls completed on the host core after a CUDA failure
+std::atomic<int> g_ndev{-1};                           // visible CUDA devices, asked once (-1 = not asked yet)
+thread_local int tl_last_error = 0;                    // per thread: clear / call / check needs no lock
 
 struct OptionDesc {
     const char* key;
@@ -93,6 +106,9 @@ const OptionDesc kOptions[] = {
     {"stage_threads", "FABE13_CUDA_STAGE_THREADS", &Config::stage_threads, 0, kSlots},
     {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 30},
     {"stream_copy", "FABE13_CUDA_STREAM_COPY", &Config::stream_copy, 0, 1},
+    {"min_n", "FABE13_CUDA_MIN_N", &Config::min_n, 0, (long long)1 << 31},
+    {"fallback", "FABE13_CUDA_FALLBACK", &Config::fallback, 0, 1},
+    {"host_threads", "FABE13_CUDA_HOST_THREADS", &Config::host_threads, 0, 256},
 };
 
 void load_env() {
@@ -129,12 +145,18 @@ LaunchTuning current_tuning() {
 
 int record(cudaError_t e, const char* where) {
     if (e == cudaSuccess) return 0;
-    g_last_error.store((int)e);
+    tl_last_error = (int)e;
     fprintf(stderr, "fabe13: CUDA error %d (%s) in %s\n", (int)e, cudaGetErrorString(e), where);
     const char* ab = getenv("FABE13_CUDA_ABORT");
     if (ab && *ab == '1') abort();
     (void)cudaGetLastError();  // clear the non-sticky error state so later calls are not poisoned
     return (int)e;
+}
+
+// an error code reported by a worker thread (recorded in ITS thread-local slot) becomes this thread's last error too
+int adopt(int rc) {
+    if (rc != 0) tl_last_error = rc;
+    return rc;
 }
 
 #define FABE13_TRY(expr)                               \
@@ -143,12 +165,53 @@ int record(cudaError_t e, const char* where) {
         if (e__ != cudaSuccess) return record(e__, #expr); \
     } while (0)
 
+// The C ABI must not let a C++ exception (std::system_error from std::thread, std::bad_alloc) cross into C callers.
+template <typename Fn>
+int guarded(const char* who, Fn fn) {
+    try {
+        return fn();
+    } catch (const std::bad_alloc&) {
+        return record(cudaErrorMemoryAllocation, who);
+    } catch (...) {
+        return record(cudaErrorUnknown, who);
+    }
+}
+
+// visible CUDA devices; asked once (a process does not gain or lose GPUs), so a box without a GPU never re-enters
+// the driver's failing initialisation on later calls
+int device_count() {
+    int n = g_ndev.load(std::memory_order_acquire);
+    if (n >= 0) return n;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        n = 0;
+    }
+    g_ndev.store(n, std::memory_order_release);
+    return n;
+}
+
+// NVTX ranges (tracing): no-ops unless a tool is attached
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
+
+int host_core_threads() {
+    long long t = g_cfg.host_threads.load();
+    if (t <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        t = hw ? (hw > 16 ? 16 : hw) : 1;
+    }
+    return (int)t;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // per-device state, created on first use (reference: load-time constructor fabe13/fabe13.c:209-214)
 // ---------------------------------------------------------------------------------------------------------------
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
     double* d_in = nullptr;   // cap elements each
     double* d_sin = nullptr;
     double* d_cos = nullptr;
@@ -167,8 +230,17 @@ struct DeviceState {
     DeviceInfo info{};
     cudaMemPool_t pool = nullptr;  // stream-ordered scratch for the device-pointer entry points
     char name[320] = {0};
-    // host path
-    std::mutex pipe_mu;
+    // host path.  Locking: a host call holds pipe_rw SHARED while its chunks are in flight, so several callers share
+    // the slots (their chunks interleave on the slots' streams; stream order keeps a slot's device buffers consistent
+    // as long as one chunk's copies and kernels are enqueued atomically: slot_mu).  Resizing or freeing slots takes
+    // pipe_rw EXCLUSIVE, i.e. waits until no call is in flight.  The pinned staging buffers of the pageable path and
+    // the small-call bounce buffer have one user at a time (stage_mu, small_mu).
+    std::shared_mutex pipe_rw;
+    std::mutex slot_mu[kSlots];
+    std::mutex stage_mu;
+    std::mutex small_mu;
+    std::mutex ev_mu;
+    std::vector<cudaEvent_t> ev_free;     // blocking-sync events: waiting host threads sleep instead of spinning
     cudaStream_t small_stream = nullptr;  // small host calls: one kernel reading/writing pinned host memory directly
     double* small_stage = nullptr;        // pinned, 3 * small_cap doubles (in | sin | cos), for pageable callers
     size_t small_cap = 0;
@@ -195,7 +267,9 @@ int device_state(int dev, DeviceState** out) {
         pp.location.type = cudaMemLocationTypeDevice;
         pp.location.id = dev;
         FABE13_TRY(cudaMemPoolCreate(&s.pool, &pp));
-        unsigned long long keep = ~0ull;  // never trim: the worklist scratch is reused call after call
+        // the worklist scratch is reused call after call (125 MB for a 1e9-element launch): keep up to two of those
+        // between calls and give the rest back, so a GPU shared with another allocator is not drained
+        unsigned long long keep = kPoolKeepBytes;
         FABE13_TRY(cudaMemPoolSetAttribute(s.pool, cudaMemPoolAttrReleaseThreshold, &keep));
         s.ready = true;
     }
@@ -299,27 +373,51 @@ void staging_copy(void* dst, const void* src, size_t bytes) {
 
 enum PtrKind { PTR_PAGEABLE, PTR_PINNED, PTR_DEVICE };
 
-PtrKind classify(const void* p) {
+PtrKind classify_byte(const void* p, ptrdiff_t* map_delta) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         (void)cudaGetLastError();
         return PTR_PAGEABLE;
     }
     if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return PTR_DEVICE;
-    if (a.type == cudaMemoryTypeHost) return PTR_PINNED;
+    if (a.type == cudaMemoryTypeHost) {
+        if (map_delta) *map_delta = (const char*)a.devicePointer - (const char*)a.hostPointer;
+        return PTR_PINNED;
+    }
     return PTR_PAGEABLE;
 }
 
-// (re)size the first `nslots` slots of the current device for `chunk` elements; pinned staging only if asked for.
-// Capacities are kept per slot: the pinned pipeline uses kPipeSlots large slots, the staging workers up to kSlots
-// small ones.
-int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning& t, int nslots) {
-    const size_t need_ws = fabe13::workspace_bytes(chunk, t);  // depends on the tuning in force
+// What kind of memory [p, p + bytes) is.  Pinned only if the LAST byte is page-locked too and maps to the device with
+// the same offset as the first one: a pointer into a smaller cudaHostRegister region (or a sub-array reaching past the
+// end of a pinned block) is treated as pageable and staged, instead of faulting inside a copy or a zero-copy kernel.
+PtrKind classify(const void* p, size_t bytes) {
+    ptrdiff_t d0 = 0, d1 = 0;
+    const PtrKind k = classify_byte(p, &d0);
+    if (k != PTR_PINNED || bytes <= 1) return k;
+    const PtrKind k1 = classify_byte((const char*)p + bytes - 1, &d1);
+    return (k1 == PTR_PINNED && d0 == d1) ? PTR_PINNED : PTR_PAGEABLE;
+}
+
+bool slots_fit(const DeviceState& s, size_t chunk, bool device_bufs, bool staging, size_t need_ws, int nslots) {
+    for (int i = 0; i < nslots; ++i) {
+        const Slot& sl = s.slots[i];
+        if (!sl.stream) return false;
+        if (device_bufs && sl.cap < chunk) return false;
+        if (need_ws > 0 && sl.ws_bytes < need_ws) return false;
+        if (staging && sl.stage_cap < chunk) return false;
+    }
+    return true;
+}
+
+// (re)size the first `nslots` slots of the current device for `chunk` elements; pinned staging only if asked for,
+// device buffers only if asked for (the FP32 path works on its staging buffers in place).  Capacities are kept per
+// slot: the pinned pipeline uses kPipeSlots large slots, the staging workers up to kSlots small ones.
+// Caller holds pipe_rw exclusively: no call is in flight on any slot.
+int grow_slots(DeviceState& s, size_t chunk, bool device_bufs, bool staging, size_t need_ws, int nslots) {
     for (int i = 0; i < nslots; ++i) {
         Slot& sl = s.slots[i];
         if (!sl.stream) FABE13_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        if (!sl.done) FABE13_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventBlockingSync | cudaEventDisableTiming));
-        if (sl.cap < chunk) {
+        if (device_bufs && sl.cap < chunk) {
             if (sl.d_in) FABE13_TRY(cudaFree(sl.d_in));
             if (sl.d_sin) FABE13_TRY(cudaFree(sl.d_sin));
             if (sl.d_cos) FABE13_TRY(cudaFree(sl.d_cos));
@@ -352,6 +450,36 @@ int ensure_slots(DeviceState& s, size_t chunk, bool staging, const LaunchTuning&
     return 0;
 }
 
+// Returns with `lk` holding pipe_rw shared and the first nslots slots large enough.
+int acquire_slots(DeviceState& s, std::shared_lock<std::shared_mutex>& lk, size_t chunk, bool device_bufs, bool staging,
+                  size_t need_ws, int nslots) {
+    for (;;) {
+        lk.lock();
+        if (slots_fit(s, chunk, device_bufs, staging, need_ws, nslots)) return 0;
+        lk.unlock();
+        std::unique_lock<std::shared_mutex> x(s.pipe_rw);  // waits for the calls in flight
+        if (int rc = grow_slots(s, chunk, device_bufs, staging, need_ws, nslots)) return rc;
+    }
+}
+
+int take_event(DeviceState& s, cudaEvent_t* ev) {
+    {
+        std::lock_guard<std::mutex> lk(s.ev_mu);
+        if (!s.ev_free.empty()) {
+            *ev = s.ev_free.back();
+            s.ev_free.pop_back();
+            return 0;
+        }
+    }
+    FABE13_TRY(cudaEventCreateWithFlags(ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    return 0;
+}
+
+void give_event(DeviceState& s, cudaEvent_t ev) {
+    std::lock_guard<std::mutex> lk(s.ev_mu);
+    s.ev_free.push_back(ev);
+}
+
 size_t pick_chunk(size_t n) {
     const size_t cap = (size_t)g_cfg.chunk_elems.load();
     size_t c = (n + 5) / 6;  // at least ~6 chunks so the three stages overlap
@@ -361,17 +489,28 @@ size_t pick_chunk(size_t n) {
     return (c + 3) & ~(size_t)3;
 }
 
-// enqueue one chunk on a slot: H2D, kernels, 2x D2H.  src/dst are pinned (user memory or staging).
-int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, double* dst_cos, size_t m,
-                  const LaunchTuning& t, int core, int op) {
-    FABE13_TRY(cudaMemcpyAsync(sl.d_in, src, m * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
-    int launches = 0;
-    cudaError_t e = fabe13::launch_sincos(sl.d_in, dst_sin ? sl.d_sin : nullptr, dst_cos ? sl.d_cos : nullptr, nullptr, m, op, core,
-                                          t, s.info, (m >= (size_t)t.small_n && fabe13::workspace_bytes(m, t) > 0) ? sl.d_ws : nullptr, sl.stream, &launches);
-    g_launches.fetch_add((unsigned long long)launches);
-    if (e != cudaSuccess) return record(e, "launch_sincos(host path)");
+// enqueue one chunk on a slot: H2D, kernels, 2x D2H (then `done`, if given).  src/dst are pinned (user memory or
+// staging).  The slot's mutex makes the sequence atomic with respect to other callers sharing the slot.
+int enqueue_chunk(DeviceState& s, int slot, const double* src, double* dst_sin, double* dst_cos, size_t m,
+                  const LaunchTuning& t, int core, int op, cudaEvent_t done) {
+    Slot& sl = s.slots[slot];
+    std::lock_guard<std::mutex> lk(s.slot_mu[slot]);
+    {
+        Range r("fabe13:h2d");
+        FABE13_TRY(cudaMemcpyAsync(sl.d_in, src, m * sizeof(double), cudaMemcpyHostToDevice, sl.stream));
+    }
+    {
+        Range r("fabe13:kernel");
+        int launches = 0;
+        cudaError_t e = fabe13::launch_sincos(sl.d_in, dst_sin ? sl.d_sin : nullptr, dst_cos ? sl.d_cos : nullptr, nullptr, m, op, core,
+                                              t, s.info, (m >= (size_t)t.small_n && fabe13::workspace_bytes(m, t) > 0) ? sl.d_ws : nullptr, sl.stream, &launches);
+        g_launches.fetch_add((unsigned long long)launches);
+        if (e != cudaSuccess) return record(e, "launch_sincos(host path)");
+    }
+    Range r("fabe13:d2h");
     if (dst_sin) FABE13_TRY(cudaMemcpyAsync(dst_sin, sl.d_sin, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
     if (dst_cos) FABE13_TRY(cudaMemcpyAsync(dst_cos, sl.d_cos, m * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+    if (done) FABE13_TRY(cudaEventRecord(done, sl.stream));
     return 0;
 }
 
@@ -381,6 +520,8 @@ int enqueue_chunk(DeviceState& s, Slot& sl, const double* src, double* dst_sin, 
 // (memory registered without a device mapping), in which case the caller takes the copy pipeline.
 int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned,
                const LaunchTuning& t, int core, int op) {
+    Range range("fabe13:zero_copy");
+    std::lock_guard<std::mutex> lk(s.small_mu);
     if (!s.small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&s.small_stream, cudaStreamNonBlocking));
     const double* src = in;
     double *dst_s = sin_out, *dst_c = cos_out;  // either may be null (single-output calls)
@@ -428,11 +569,35 @@ int host_small(DeviceState& s, const double* in, double* sin_out, double* cos_ou
     return 0;
 }
 
+int default_stage_workers() {
+    int w = (int)g_cfg.stage_threads.load();
+    if (w <= 0) {
+        // the staging copies are what bounds this path (measured: throughput still grows from 8 to 12 threads on
+        // a 16-thread host), so take most of the machine; the caller's own thread is worker 0
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned want = hw - hw / 4;
+        w = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
+    }
+    return w;
+}
+
+// run work(w) for w = 0 .. workers-1, worker 0 on the calling thread
+template <typename Fn>
+void run_workers(int workers, Fn work) {
+    if (workers <= 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
+    work(0);
+    for (std::thread& x : th) x.join();
+}
+
 // One device, one contiguous slice.  Caller has made `dev` current.
 int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned, int op) {
     DeviceState* ds;
     if (int rc = device_state(dev, &ds)) return rc;
-    std::lock_guard<std::mutex> lk(ds->pipe_mu);
     const LaunchTuning t = current_tuning();
     const int core = (int)g_cfg.core.load();
     // one kernel working on host memory directly: up to zero_copy_max elements for pinned arrays (faster than the
@@ -447,50 +612,53 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
     if (!pinned) {
         // staged: pieces of at most 8 MB, and small enough that every worker gets about three of them (a worker handles
         // its pieces one after the other -- copy in, run, copy out -- so it is the other workers that overlap its stages)
-        stage_workers = (int)g_cfg.stage_threads.load();
-        if (stage_workers <= 0) {
-            // the staging copies are what bounds this path (measured: throughput still grows from 8 to 12 threads on
-            // a 16-thread host), so take most of the machine; the caller's own thread is worker 0
-            const unsigned hw = std::thread::hardware_concurrency();
-            const unsigned want = hw - hw / 4;
-            stage_workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
-        }
+        stage_workers = default_stage_workers();
         chunk = n / ((size_t)stage_workers * 3);
         if (chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;
         if (chunk < ((size_t)1 << 16)) chunk = (size_t)1 << 16;
         chunk = (chunk + 3) & ~(size_t)3;
     }
     const size_t nchunks = (n + chunk - 1) / chunk;
+    const size_t need_ws = fabe13::workspace_bytes(chunk, t);  // depends on the tuning in force
+    const bool sleep_wait = n >= ((size_t)1 << 22);  // long waits: sleep on a blocking event; short ones: spin (lower latency)
 
     if (pinned) {
-        if (int rc = ensure_slots(*ds, chunk, false, t, kPipeSlots)) return rc;
+        Range range("fabe13:pinned_pipeline");
+        std::shared_lock<std::shared_mutex> lk(ds->pipe_rw, std::defer_lock);
+        if (int rc = acquire_slots(*ds, lk, chunk, true, false, need_ws, kPipeSlots)) return rc;
         // copy engines read and write the caller's pinned memory directly; one host thread feeds all slots
-        for (size_t i = 0; i < nchunks; ++i) {
+        cudaEvent_t ev[kPipeSlots] = {};
+        const int used = nchunks < (size_t)kPipeSlots ? (int)nchunks : kPipeSlots;
+        int rc = 0;
+        if (sleep_wait)
+            for (int i = 0; i < used && rc == 0; ++i) rc = take_event(*ds, &ev[i]);
+        for (size_t i = 0; i < nchunks && rc == 0; ++i) {
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
-            if (int rc = enqueue_chunk(*ds, ds->slots[i % kPipeSlots], in + off, sin_out ? sin_out + off : nullptr,
-                                       cos_out ? cos_out + off : nullptr, m, t, core, op)) {
-                // earlier chunks are still copying into the caller's arrays: do not hand the arrays back mid-flight
-                for (int j = 0; j < kPipeSlots; ++j) (void)cudaStreamSynchronize(ds->slots[j].stream);
-                (void)cudaGetLastError();
-                return rc;
-            }
+            const int slot = (int)(i % kPipeSlots);
+            rc = enqueue_chunk(*ds, slot, in + off, sin_out ? sin_out + off : nullptr, cos_out ? cos_out + off : nullptr, m,
+                               t, core, op, ev[slot]);
         }
-        if (n >= ((size_t)1 << 22)) {
-            // large transfers: sleep on blocking events rather than spin (the wait is milliseconds long)
-            for (int i = 0; i < kPipeSlots; ++i) FABE13_TRY(cudaEventRecord(ds->slots[i].done, ds->slots[i].stream));
-            for (int i = 0; i < kPipeSlots; ++i) FABE13_TRY(cudaEventSynchronize(ds->slots[i].done));
-        } else {
-            for (int i = 0; i < kPipeSlots; ++i) FABE13_TRY(cudaStreamSynchronize(ds->slots[i].stream));
+        // (also after a failure: earlier chunks are still copying into the caller's arrays -- do not hand the arrays
+        // back mid-flight)
+        for (int i = 0; i < used; ++i) {
+            cudaError_t e = (sleep_wait && ev[i] && rc == 0) ? cudaEventSynchronize(ev[i]) : cudaStreamSynchronize(ds->slots[i].stream);
+            if (e != cudaSuccess && rc == 0) rc = record(e, "wait for the pipeline");
         }
-        return 0;
+        for (int i = 0; i < used; ++i)
+            if (ev[i]) give_event(*ds, ev[i]);
+        if (rc != 0) (void)cudaGetLastError();
+        return rc;
     }
 
     // pageable memory: worker w owns slot w and the chunks i = w (mod workers); it copies the chunk into pinned
     // staging, runs it, waits, and copies the results out.  Workers overlap each other's stages.
+    Range range("fabe13:staged_pipeline");
     int workers = stage_workers;
     if ((size_t)workers > nchunks) workers = (int)nchunks;
-    if (int rc = ensure_slots(*ds, chunk, true, t, workers)) return rc;
+    std::lock_guard<std::mutex> stage_lk(ds->stage_mu);
+    std::shared_lock<std::shared_mutex> lk(ds->pipe_rw, std::defer_lock);
+    if (int rc = acquire_slots(*ds, lk, chunk, true, true, need_ws, workers)) return rc;
     std::atomic<int> rc_all{0};
     auto work = [&](int w) {
         if (cudaSetDevice(dev) != cudaSuccess) {
@@ -498,47 +666,59 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             return;
         }
         Slot& sl = ds->slots[w];
+        cudaEvent_t ev = nullptr;
+        if (sleep_wait && take_event(*ds, &ev) != 0) {
+            rc_all.store(tl_last_error);
+            return;
+        }
         for (size_t i = (size_t)w; i < nchunks && rc_all.load() == 0; i += (size_t)workers) {
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
-            staging_copy(sl.h_in, in + off, m * sizeof(double));
-            int rc = enqueue_chunk(*ds, sl, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core, op);
+            {
+                Range r("fabe13:stage_in");
+                staging_copy(sl.h_in, in + off, m * sizeof(double));
+            }
+            int rc = enqueue_chunk(*ds, w, sl.h_in, sin_out ? sl.h_sin : nullptr, cos_out ? sl.h_cos : nullptr, m, t, core, op, ev);
             if (rc == 0) {
-                cudaError_t e;
-                if (n >= ((size_t)1 << 22)) {  // long waits: sleep on a blocking event; short ones: spin (lower latency)
-                    e = cudaEventRecord(sl.done, sl.stream);
-                    if (e == cudaSuccess) e = cudaEventSynchronize(sl.done);
-                } else {
-                    e = cudaStreamSynchronize(sl.stream);
-                }
+                const cudaError_t e = ev ? cudaEventSynchronize(ev) : cudaStreamSynchronize(sl.stream);
                 if (e != cudaSuccess) rc = record(e, "wait for chunk (worker)");
             }
             if (rc != 0) {
                 rc_all.store(rc);
-                return;
+                break;
             }
+            Range r("fabe13:stage_out");
             if (sin_out) staging_copy(sin_out + off, sl.h_sin, m * sizeof(double));
             if (cos_out) staging_copy(cos_out + off, sl.h_cos, m * sizeof(double));
         }
+        if (ev) give_event(*ds, ev);
     };
-    if (workers <= 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
-        work(0);
-        for (std::thread& x : th) x.join();
-    }
-    return rc_all.load();
+    run_workers(workers, work);
+    return adopt(rc_all.load());
+}
+
+// host-pointer calls below "min_n" elements: the host instantiation of the per-element core (one thread, no CUDA call
+// beyond finding out that `in` is not a device pointer).  Reference: the n < 32 scalar route, fabe13/fabe13.c:226-229.
+bool stays_on_host(const void* in, size_t n) {
+    if (n >= (size_t)g_cfg.min_n.load(std::memory_order_relaxed)) return false;
+    return device_count() == 0 || classify_byte(in, nullptr) != PTR_DEVICE;
 }
 
 int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int op = FABE13_OP_SINCOS) {
     if (n == 0) return 0;
     load_env();
-    if (!sin_out && !cos_out) return record(cudaErrorInvalidValue, "no output array");
-    const PtrKind ki = classify(in);
-    const PtrKind ks = sin_out ? classify(sin_out) : classify(cos_out);
-    const PtrKind kc = cos_out ? classify(cos_out) : ks;
+    if (!in || (!sin_out && !cos_out)) return record(cudaErrorInvalidValue, "null array");
+    if (stays_on_host(in, n)) {
+        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), 1);
+        g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
+    if (device_count() == 0) return record(cudaErrorNoDevice, "no CUDA device is visible");
+    Range range("fabe13_sincos_host");
+    const size_t bytes = n * sizeof(double);
+    const PtrKind ki = classify(in, bytes);
+    const PtrKind ks = sin_out ? classify(sin_out, bytes) : classify(cos_out, bytes);
+    const PtrKind kc = cos_out ? classify(cos_out, bytes) : ks;
     if (ki == PTR_DEVICE || ks == PTR_DEVICE || kc == PTR_DEVICE) {
         if (!(ki == PTR_DEVICE && ks == PTR_DEVICE && kc == PTR_DEVICE))
             return record(cudaErrorInvalidValue, "fabe13_sincos: mixed host and device pointers");
@@ -549,8 +729,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
     const bool pinned = (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED);
     int cur = 0;
     FABE13_TRY(cudaGetDevice(&cur));
-    int ndev_avail = 0;
-    FABE13_TRY(cudaGetDeviceCount(&ndev_avail));
+    const int ndev_avail = device_count();
     int ndev = (int)g_cfg.host_devices.load();
     if (ndev > ndev_avail) ndev = ndev_avail;
     if (ndev <= 1 || n < ((size_t)1 << 20)) return host_slice(cur, in, sin_out, cos_out, n, pinned, op);
@@ -573,7 +752,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
     }
     for (std::thread& x : th) x.join();
     for (int rc : rcs)
-        if (rc) return rc;
+        if (rc) return adopt(rc);
     return 0;
 }
 
@@ -600,7 +779,15 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     if (n == 0) return 0;
     load_env();
     if (!in || !sin_out || !cos_out) return record(cudaErrorInvalidValue, "fabe13_sincosf_host: null array");
-    const PtrKind ki = classify(in), ks = classify(sin_out), kc = classify(cos_out);
+    if (stays_on_host(in, n)) {
+        fabe13::host_sincosf_array(in, sin_out, cos_out, n, (int)g_cfg.core.load(), 1);
+        g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
+    if (device_count() == 0) return record(cudaErrorNoDevice, "no CUDA device is visible");
+    Range range("fabe13_sincosf_host");
+    const size_t bytes = n * sizeof(float);
+    const PtrKind ki = classify(in, bytes), ks = classify(sin_out, bytes), kc = classify(cos_out, bytes);
     if (ki == PTR_DEVICE || ks == PTR_DEVICE || kc == PTR_DEVICE) {
         if (!(ki == PTR_DEVICE && ks == PTR_DEVICE && kc == PTR_DEVICE))
             return record(cudaErrorInvalidValue, "fabe13_sincosf_host: mixed host and device pointers");
@@ -610,12 +797,12 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     }
     DeviceState* ds;
     if (int rc = current_device_state(&ds)) return rc;
-    std::lock_guard<std::mutex> lk(ds->pipe_mu);
-    if (!ds->small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&ds->small_stream, cudaStreamNonBlocking));
     if (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED) {
         void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
         if (cudaHostGetDevicePointer(&d_in, (void*)in, 0) == cudaSuccess && cudaHostGetDevicePointer(&d_s, sin_out, 0) == cudaSuccess &&
             cudaHostGetDevicePointer(&d_c, cos_out, 0) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(ds->small_mu);
+            if (!ds->small_stream) FABE13_TRY(cudaStreamCreateWithFlags(&ds->small_stream, cudaStreamNonBlocking));
             if (int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, n, ds->small_stream)) return rc;
             FABE13_TRY(cudaStreamSynchronize(ds->small_stream));
             return 0;
@@ -625,12 +812,7 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     // pageable memory: like the FP64 path, worker w owns slot w (its pinned staging buffers and its stream) and the
     // pieces i = w (mod workers): copy in, one kernel over the staging buffers in place (zero-copy over PCIe), copy out.
     // The staging copies bound this path (host memory bandwidth), hence the threads.
-    int workers = (int)g_cfg.stage_threads.load();
-    if (workers <= 0) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned want = hw - hw / 4;
-        workers = (int)(want > (unsigned)kSlots ? (unsigned)kSlots : (want ? want : 1));
-    }
+    int workers = default_stage_workers();
     // pieces of at most 8 MB per staging buffer, small enough that every worker gets about three of them
     size_t piece = n / ((size_t)workers * 3);                     // floats per piece
     if (piece > ((size_t)1 << 21)) piece = (size_t)1 << 21;
@@ -639,8 +821,9 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     const size_t piece_doubles = (piece * sizeof(float) + sizeof(double) - 1) / sizeof(double);  // buffers are sized in doubles
     const size_t npieces = (n + piece - 1) / piece;
     if ((size_t)workers > npieces) workers = (int)npieces;
-    const LaunchTuning t = current_tuning();
-    if (int rc = ensure_slots(*ds, piece_doubles, true, t, workers)) return rc;
+    std::lock_guard<std::mutex> stage_lk(ds->stage_mu);
+    std::shared_lock<std::shared_mutex> lk(ds->pipe_rw, std::defer_lock);
+    if (int rc = acquire_slots(*ds, lk, piece_doubles, false, true, 0, workers)) return rc;  // staging only: no device buffers
     int dev = 0;
     FABE13_TRY(cudaGetDevice(&dev));
     std::atomic<int> rc_all{0};
@@ -663,7 +846,11 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
             const size_t off = i * piece;
             const size_t m = n - off < piece ? n - off : piece;
             staging_copy(h_in, in + off, m * sizeof(float));
-            int rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, m, sl.stream);
+            int rc;
+            {
+                std::lock_guard<std::mutex> slot_lk(ds->slot_mu[w]);
+                rc = run_device_f32((const float*)d_in, (float*)d_s, (float*)d_c, m, sl.stream);
+            }
             if (rc == 0) {
                 cudaError_t e = cudaStreamSynchronize(sl.stream);
                 if (e != cudaSuccess) rc = record(e, "wait for piece (worker)");
@@ -676,39 +863,13 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
             staging_copy(cos_out + off, h_c, m * sizeof(float));
         }
     };
-    if (workers <= 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
-        work(0);
-        for (std::thread& x : th) x.join();
-    }
-    return rc_all.load();
+    run_workers(workers, work);
+    return adopt(rc_all.load());
 }
 
 int cfg_core() {
     load_env();
     return (int)g_cfg.core.load();
-}
-
-void host_one(double x, int core, double* s, double* c, long long* k) {
-    uint64_t sb, cb;
-    int64_t kk;
-    if (core == FABE13_CORE_PSI)
-        fabe13_sincos_one<FABE13_CORE_PSI>(fabe13_bits(x), h_ph_stream, &sb, &cb, &kk);
-    else
-        fabe13_sincos_one<FABE13_CORE_POLY>(fabe13_bits(x), h_ph_stream, &sb, &cb, &kk);
-    *s = fabe13_from_bits(sb);
-    *c = fabe13_from_bits(cb);
-    if (k) *k = (long long)kk;
-}
-
-template <int OP>
-double host_derived(double x) {
-    double s, c;
-    host_one(x, cfg_core(), &s, &c, nullptr);
-    return fabe13_from_bits(fabe13_derived<OP>(fabe13_bits(x), fabe13_bits(s), fabe13_bits(c)));
 }
 
 int derived_device(const double* d_in, double* d_out, size_t n, void* cuda_stream, int op, const char* who) {
@@ -722,6 +883,77 @@ int derived_host(const double* in, double* out, size_t n, int op, const char* wh
     return run_host(in, out, nullptr, n, op);
 }
 
+// give back what the host path holds on one device (caller made it current): slot buffers, pinned staging, the bounce
+// buffer, the pool's cached scratch.  With `destroy`, also streams, events and the pool itself.
+int release_device(DeviceState& s, bool destroy) {
+    std::lock_guard<std::mutex> init_lk(s.init_mu);
+    if (!s.ready) return 0;
+    std::lock_guard<std::mutex> stage_lk(s.stage_mu);        // same order as the staged paths: stage_mu, then pipe_rw
+    std::unique_lock<std::shared_mutex> pipe_lk(s.pipe_rw);  // waits for host calls in flight
+    std::lock_guard<std::mutex> small_lk(s.small_mu);
+    int rc = 0;
+    auto keep = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == 0) rc = record(e, what);
+    };
+    for (Slot& sl : s.slots) {
+        if (sl.stream) keep(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize(slot)");
+        if (sl.d_in) keep(cudaFree(sl.d_in), "cudaFree(slot)");
+        if (sl.d_sin) keep(cudaFree(sl.d_sin), "cudaFree(slot)");
+        if (sl.d_cos) keep(cudaFree(sl.d_cos), "cudaFree(slot)");
+        if (sl.d_ws) keep(cudaFree(sl.d_ws), "cudaFree(slot)");
+        if (sl.h_in) keep(cudaFreeHost(sl.h_in), "cudaFreeHost(slot)");
+        if (sl.h_sin) keep(cudaFreeHost(sl.h_sin), "cudaFreeHost(slot)");
+        if (sl.h_cos) keep(cudaFreeHost(sl.h_cos), "cudaFreeHost(slot)");
+        sl.d_in = sl.d_sin = sl.d_cos = nullptr;
+        sl.d_ws = nullptr;
+        sl.h_in = sl.h_sin = sl.h_cos = nullptr;
+        sl.cap = sl.ws_bytes = sl.stage_cap = 0;
+        if (destroy && sl.stream) {
+            keep(cudaStreamDestroy(sl.stream), "cudaStreamDestroy(slot)");
+            sl.stream = nullptr;
+        }
+    }
+    if (s.small_stream) keep(cudaStreamSynchronize(s.small_stream), "cudaStreamSynchronize(small)");
+    if (s.small_stage) keep(cudaFreeHost(s.small_stage), "cudaFreeHost(bounce)");
+    s.small_stage = nullptr;
+    s.small_cap = 0;
+    if (s.pool) keep(cudaMemPoolTrimTo(s.pool, 0), "cudaMemPoolTrimTo");
+    if (destroy) {
+        if (s.small_stream) keep(cudaStreamDestroy(s.small_stream), "cudaStreamDestroy(small)");
+        s.small_stream = nullptr;
+        {
+            std::lock_guard<std::mutex> ev_lk(s.ev_mu);
+            for (cudaEvent_t ev : s.ev_free) keep(cudaEventDestroy(ev), "cudaEventDestroy");
+            s.ev_free.clear();
+        }
+        if (s.pool) keep(cudaMemPoolDestroy(s.pool), "cudaMemPoolDestroy");
+        s.pool = nullptr;
+        s.ready = false;
+    }
+    return rc;
+}
+
+int release_all(bool destroy) {
+    if (device_count() == 0) return 0;
+    int cur = 0;
+    FABE13_TRY(cudaGetDevice(&cur));
+    int rc = 0;
+    for (int d = 0; d < kMaxDevices && d < device_count(); ++d) {
+        {
+            std::lock_guard<std::mutex> lk(g_dev[d].init_mu);
+            if (!g_dev[d].ready) continue;
+        }
+        if (cudaSetDevice(d) != cudaSuccess) {
+            (void)cudaGetLastError();
+            continue;
+        }
+        const int r = release_device(g_dev[d], destroy);
+        if (r && !rc) rc = r;
+    }
+    (void)cudaSetDevice(cur);
+    return rc;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -731,19 +963,34 @@ extern "C" {
 
 void fabe13_sincos(const double* in, double* sin_out, double* cos_out, int n) {
     if (n <= 0) return;  // reference fabe13/fabe13.c:223
-    (void)run_host(in, sin_out, cos_out, (size_t)n);
+    const int rc = guarded("fabe13_sincos", [&] { return run_host(in, sin_out, cos_out, (size_t)n); });
+    if (rc == 0) return;
+    // The reference's ABI cannot report a failure (void, fabe13/fabe13.h:51-56): rather than leave the outputs
+    // unwritten, fill them with the host instantiation of the same core (same bits).  The error stays recorded.
+    if (g_cfg.fallback.load() == 0 || !in || !sin_out || !cos_out) return;
+    if (device_count() != 0 && (classify_byte(in, nullptr) == PTR_DEVICE || classify_byte(sin_out, nullptr) == PTR_DEVICE ||
+                                classify_byte(cos_out, nullptr) == PTR_DEVICE))
+        return;  // device memory: nothing the host can do
+    const int rc2 = guarded("fabe13_sincos (host fallback)", [&] {
+        fabe13::host_sincos_array(in, sin_out, cos_out, (size_t)n, FABE13_OP_SINCOS, cfg_core(), host_core_threads());
+        return 0;
+    });
+    if (rc2 == 0) {
+        g_fallbacks.fetch_add(1);
+        tl_last_error = rc;  // what went wrong on the CUDA side stays visible
+    }
 }
 
 int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n) {
-    return run_host(in, sin_out, cos_out, n);
+    return guarded("fabe13_sincos_host", [&] { return run_host(in, sin_out, cos_out, n); });
 }
 
 const char* fabe13_get_active_implementation_name(void) {
+    static char host_name[160];
     DeviceState* ds;
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-        (void)cudaGetLastError();
-        return "CUDA sm_100a (no device visible)";
+    if (device_count() == 0) {
+        snprintf(host_name, sizeof host_name, "CUDA sm_100a (no device visible; host core %s)", fabe13::host_isa_name());
+        return host_name;
     }
     if (current_device_state(&ds) != 0) return "CUDA sm_100a (device initialisation failed)";
     return ds->name;
@@ -754,71 +1001,79 @@ int fabe13_get_active_simd_width(void) { return 32; }
 // scalar API: host instantiation of the array core (reference fabe13/fabe13.c:262-269)
 double fabe13_sin(double x) {
     double s, c;
-    host_one(x, cfg_core(), &s, &c, nullptr);
+    fabe13::host_sincos_one(x, cfg_core(), &s, &c, nullptr);
     return s;
 }
 double fabe13_cos(double x) {
     double s, c;
-    host_one(x, cfg_core(), &s, &c, nullptr);
+    fabe13::host_sincos_one(x, cfg_core(), &s, &c, nullptr);
     return c;
 }
 // sinc / tan / cot: the reference's guards (fabe13/fabe13.c:264-266: |x| < 1e-9 -> 1, cos == 0 -> NAN, sin == 0 -> NAN)
 // around one division; the same fabe13_derived the array kernels compile for the device
-double fabe13_sinc(double x) { return host_derived<FABE13_OP_SINC>(x); }
-double fabe13_tan(double x) { return host_derived<FABE13_OP_TAN>(x); }
-double fabe13_cot(double x) { return host_derived<FABE13_OP_COT>(x); }
+double fabe13_sinc(double x) { return fabe13::host_derived_one(x, FABE13_OP_SINC, cfg_core()); }
+double fabe13_tan(double x) { return fabe13::host_derived_one(x, FABE13_OP_TAN, cfg_core()); }
+double fabe13_cot(double x) { return fabe13::host_derived_one(x, FABE13_OP_COT, cfg_core()); }
 double fabe13_atan(double x) { return atan(x); }
 double fabe13_asin(double x) { return asin(x); }
 double fabe13_acos(double x) { return acos(x); }
 
 int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream) {
-    return run_device(d_in, d_sin, d_cos, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+    return guarded("fabe13_sincos_device", [&] { return run_device(d_in, d_sin, d_cos, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream); });
 }
 
 // single-output array variants (the array forms of fabe13_sin / fabe13_cos): 16 B/element instead of 24
 int fabe13_sin_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
     if (!d_out && n) return record(cudaErrorInvalidValue, "fabe13_sin_device: null output");
-    return run_device(d_in, d_out, nullptr, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+    return guarded("fabe13_sin_device", [&] { return run_device(d_in, d_out, nullptr, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream); });
 }
 int fabe13_cos_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
     if (!d_out && n) return record(cudaErrorInvalidValue, "fabe13_cos_device: null output");
-    return run_device(d_in, nullptr, d_out, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream);
+    return guarded("fabe13_cos_device", [&] { return run_device(d_in, nullptr, d_out, nullptr, n, nullptr, 0, (cudaStream_t)cuda_stream); });
 }
 int fabe13_sin_host(const double* in, double* out, size_t n) {
     if (n == 0) return 0;
     if (!out) return record(cudaErrorInvalidValue, "fabe13_sin_host: null output");
-    return run_host(in, out, nullptr, n);
+    return guarded("fabe13_sin_host", [&] { return run_host(in, out, nullptr, n); });
 }
 int fabe13_cos_host(const double* in, double* out, size_t n) {
     if (n == 0) return 0;
     if (!out) return record(cudaErrorInvalidValue, "fabe13_cos_host: null output");
-    return run_host(in, nullptr, out, n);
+    return guarded("fabe13_cos_host", [&] { return run_host(in, nullptr, out, n); });
 }
 
 // array forms of fabe13_tan / fabe13_cot / fabe13_sinc: the same per-element code as the scalar entry points
 int fabe13_tan_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
-    return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_TAN, "fabe13_tan_device: null output");
+    return guarded("fabe13_tan_device", [&] { return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_TAN, "fabe13_tan_device: null output"); });
 }
 int fabe13_cot_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
-    return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_COT, "fabe13_cot_device: null output");
+    return guarded("fabe13_cot_device", [&] { return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_COT, "fabe13_cot_device: null output"); });
 }
 int fabe13_sinc_device(const double* d_in, double* d_out, size_t n, void* cuda_stream) {
-    return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_SINC, "fabe13_sinc_device: null output");
+    return guarded("fabe13_sinc_device", [&] { return derived_device(d_in, d_out, n, cuda_stream, FABE13_OP_SINC, "fabe13_sinc_device: null output"); });
 }
-int fabe13_tan_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_TAN, "fabe13_tan_host: null output"); }
-int fabe13_cot_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_COT, "fabe13_cot_host: null output"); }
-int fabe13_sinc_host(const double* in, double* out, size_t n) { return derived_host(in, out, n, FABE13_OP_SINC, "fabe13_sinc_host: null output"); }
+int fabe13_tan_host(const double* in, double* out, size_t n) {
+    return guarded("fabe13_tan_host", [&] { return derived_host(in, out, n, FABE13_OP_TAN, "fabe13_tan_host: null output"); });
+}
+int fabe13_cot_host(const double* in, double* out, size_t n) {
+    return guarded("fabe13_cot_host", [&] { return derived_host(in, out, n, FABE13_OP_COT, "fabe13_cot_host: null output"); });
+}
+int fabe13_sinc_host(const double* in, double* out, size_t n) {
+    return guarded("fabe13_sinc_host", [&] { return derived_host(in, out, n, FABE13_OP_SINC, "fabe13_sinc_host: null output"); });
+}
 
 // FP32 arrays (the reference's roadmap item README.md:225; no reference implementation exists)
 int fabe13_sincosf_device(const float* d_in, float* d_sin, float* d_cos, size_t n, void* cuda_stream) {
     if (n && (!d_in || !d_sin || !d_cos)) return record(cudaErrorInvalidValue, "fabe13_sincosf_device: null array");
-    return run_device_f32(d_in, d_sin, d_cos, n, (cudaStream_t)cuda_stream);
+    return guarded("fabe13_sincosf_device", [&] { return run_device_f32(d_in, d_sin, d_cos, n, (cudaStream_t)cuda_stream); });
 }
-int fabe13_sincosf_host(const float* in, float* sin_out, float* cos_out, size_t n) { return run_host_f32(in, sin_out, cos_out, n); }
+int fabe13_sincosf_host(const float* in, float* sin_out, float* cos_out, size_t n) {
+    return guarded("fabe13_sincosf_host", [&] { return run_host_f32(in, sin_out, cos_out, n); });
+}
 
 int fabe13_sincos_device_k(const double* d_in, double* d_sin, double* d_cos, long long* d_k, size_t n,
                            void* cuda_stream) {
-    return run_device(d_in, d_sin, d_cos, d_k, n, nullptr, 0, (cudaStream_t)cuda_stream);
+    return guarded("fabe13_sincos_device_k", [&] { return run_device(d_in, d_sin, d_cos, d_k, n, nullptr, 0, (cudaStream_t)cuda_stream); });
 }
 
 size_t fabe13_sincos_workspace_bytes(size_t n) {
@@ -830,34 +1085,37 @@ int fabe13_sincos_device_ws(const double* d_in, double* d_sin, double* d_cos, si
                             size_t workspace_bytes, void* cuda_stream) {
     if (!workspace && fabe13_sincos_workspace_bytes(n) > 0)
         return record(cudaErrorInvalidValue, "fabe13_sincos_device_ws: null workspace");
-    return run_device(d_in, d_sin, d_cos, nullptr, n, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+    return guarded("fabe13_sincos_device_ws",
+                   [&] { return run_device(d_in, d_sin, d_cos, nullptr, n, workspace, workspace_bytes, (cudaStream_t)cuda_stream); });
 }
 
 int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in, double* const* d_sin,
                         double* const* d_cos, const size_t* n_per_dev) {
-    int cur = 0;
-    FABE13_TRY(cudaGetDevice(&cur));
-    int rc = 0;
-    for (int g = 0; g < ngpu && rc == 0; ++g) {
-        cudaError_t e = cudaSetDevice(devices[g]);
-        if (e != cudaSuccess) {
-            rc = record(e, "cudaSetDevice(multi)");
-            break;
+    return guarded("fabe13_sincos_multi", [&]() -> int {
+        int cur = 0;
+        FABE13_TRY(cudaGetDevice(&cur));
+        int rc = 0;
+        for (int g = 0; g < ngpu && rc == 0; ++g) {
+            cudaError_t e = cudaSetDevice(devices[g]);
+            if (e != cudaSuccess) {
+                rc = record(e, "cudaSetDevice(multi)");
+                break;
+            }
+            rc = run_device(d_in[g], d_sin[g], d_cos[g], nullptr, n_per_dev[g], nullptr, 0, nullptr);
         }
-        rc = run_device(d_in[g], d_sin[g], d_cos[g], nullptr, n_per_dev[g], nullptr, 0, nullptr);
-    }
-    for (int g = 0; g < ngpu; ++g) {
-        if (cudaSetDevice(devices[g]) != cudaSuccess) continue;
-        cudaError_t e = cudaStreamSynchronize(nullptr);
-        if (e != cudaSuccess && rc == 0) rc = record(e, "cudaStreamSynchronize(multi)");
-    }
-    (void)cudaSetDevice(cur);
-    return rc;
+        for (int g = 0; g < ngpu; ++g) {
+            if (cudaSetDevice(devices[g]) != cudaSuccess) continue;
+            cudaError_t e = cudaStreamSynchronize(nullptr);
+            if (e != cudaSuccess && rc == 0) rc = record(e, "cudaStreamSynchronize(multi)");
+        }
+        (void)cudaSetDevice(cur);
+        return rc;
+    });
 }
 
 void* fabe13_cuda_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         record(cudaErrorMemoryAllocation, "fabe13_cuda_host_alloc");
         return nullptr;
     }
@@ -877,6 +1135,14 @@ int fabe13_cuda_host_register(void* p, size_t bytes) {
 int fabe13_cuda_host_unregister(void* p) {
     FABE13_TRY(cudaHostUnregister(p));
     return 0;
+}
+
+int fabe13_cuda_trim(void) {
+    return guarded("fabe13_cuda_trim", [] { return release_all(false); });
+}
+
+int fabe13_cuda_shutdown(void) {
+    return guarded("fabe13_cuda_shutdown", [] { return release_all(true); });
 }
 
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end) {
@@ -914,6 +1180,14 @@ int fabe13_cuda_get_option(const char* key, long long* value) {
         *value = (long long)g_launches.load();
         return 0;
     }
+    if (strcmp(key, "host_core_calls") == 0) {
+        *value = (long long)g_host_core_calls.load();
+        return 0;
+    }
+    if (strcmp(key, "fallbacks") == 0) {
+        *value = (long long)g_fallbacks.load();
+        return 0;
+    }
     if (strcmp(key, "device_count") == 0) {
         *value = fabe13_cuda_device_count();
         return 0;
@@ -927,40 +1201,29 @@ int fabe13_cuda_get_option(const char* key, long long* value) {
     return -1;
 }
 
-int fabe13_cuda_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return 0;
-    }
-    return n;
-}
+int fabe13_cuda_device_count(void) { return device_count(); }
 
-int fabe13_cuda_last_error(void) { return g_last_error.load(); }
+int fabe13_cuda_last_error(void) { return tl_last_error; }
 
-const char* fabe13_cuda_last_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_error.load()); }
+const char* fabe13_cuda_last_error_string(void) { return cudaGetErrorString((cudaError_t)tl_last_error); }
 
-void fabe13_cuda_clear_error(void) { g_last_error.store(0); }
+void fabe13_cuda_clear_error(void) { tl_last_error = 0; }
 
 void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, long long* k_out, size_t n, int core) {
-    for (size_t i = 0; i < n; ++i) host_one(in[i], core, &sin_out[i], &cos_out[i], k_out ? &k_out[i] : nullptr);
+    for (size_t i = 0; i < n; ++i) fabe13::host_sincos_one(in[i], core, &sin_out[i], &cos_out[i], k_out ? &k_out[i] : nullptr);
 }
 
 void fabe13_debug_host_sincosf(const float* in, float* sin_out, float* cos_out, size_t n, int core) {
-    for (size_t i = 0; i < n; ++i) {
-        if (core == FABE13_CORE_PSI)
-            fabe13_sincosf_one<FABE13_CORE_PSI>(in[i], h_ph_stream, &sin_out[i], &cos_out[i]);
-        else
-            fabe13_sincosf_one<FABE13_CORE_POLY>(in[i], h_ph_stream, &sin_out[i], &cos_out[i]);
-    }
+    for (size_t i = 0; i < n; ++i) fabe13::host_sincosf_one(in[i], core, &sin_out[i], &cos_out[i]);
 }
 
 void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, int core) {
-    for (size_t i = 0; i < n; ++i) {
-        double s, c;
-        host_one(in[i], core, &s, &c, nullptr);
-        out[i] = fabe13_from_bits(fabe13_derived_rt(op, fabe13_bits(in[i]), fabe13_bits(s), fabe13_bits(c)));
-    }
+    for (size_t i = 0; i < n; ++i) out[i] = fabe13::host_derived_one(in[i], op, core);
+}
+
+// the host array loop (vectorised clones + patching) as the product calls it, for CPU-only tests of that code
+void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads) {
+    fabe13::host_sincos_array(in, sin_out, cos_out, n, op, core, threads);
 }
 
 int fabe13_debug_fill_uniform_device(double* d_out, size_t n, unsigned long long seed, unsigned long long first_index,

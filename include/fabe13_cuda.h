@@ -84,6 +84,16 @@ int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in,
  * one per GPU. */
 int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n);
 
+/* Which host-pointer calls run where.  Below option "min_n" elements (default 8192; FABE13_CUDA_MIN_N) a host-pointer
+ * call -- fabe13_sincos and every *_host entry -- is evaluated on the calling thread by the HOST instantiation of the same
+ * per-element core the kernels compile for the device (bit-identical results), because a kernel launch plus a
+ * synchronisation costs ~13 us and the host core ~2 ns per element.  This mirrors the reference's own small-n route
+ * (fabe13/fabe13.c:226-229: n < 32 -> scalar loop).  "min_n" = 0 sends every call to the GPU.
+ * On a CUDA failure every int entry point returns the cudaError_t and leaves the outputs unspecified; the void
+ * fabe13_sincos(), which has no error channel (fabe13/fabe13.h:51-56), then fills sin_out / cos_out on the host core
+ * (option "fallback" = 1, the default; "host_threads" threads) and the error stays readable through
+ * fabe13_cuda_last_error().  Read-only counters: "host_core_calls", "fallbacks". */
+
 /* Pinned host allocations for the fast host path. */
 void* fabe13_cuda_host_alloc(size_t bytes);
 void fabe13_cuda_host_free(void* p);
@@ -93,6 +103,14 @@ void fabe13_cuda_host_free(void* p);
  * over the same bytes, so it pays for buffers that are reused.  Thin wrappers over cudaHostRegister/Unregister. */
 int fabe13_cuda_host_register(void* p, size_t bytes);
 int fabe13_cuda_host_unregister(void* p);
+
+/* Give back what the library holds between calls: the host pipeline's device buffers (up to 8 slots x 3 x chunk), its
+ * pinned staging buffers, the small-call bounce buffer and the cached scratch of the stream-ordered pool (which keeps
+ * at most 256 MB on its own).  _trim keeps streams and events, so the next call only re-allocates buffers; _shutdown
+ * also destroys streams, events and the pool (the library re-initialises on the next call).  Both wait for host-pointer
+ * calls in flight; do not call them concurrently with device-pointer calls on other threads. */
+int fabe13_cuda_trim(void);
+int fabe13_cuda_shutdown(void);
 
 /* Contiguous slice [begin, end) of an n-element array owned by `rank` of `world` ranks; interior boundaries are
  * multiples of 4 elements so every slice keeps 32-byte alignment.  The remainder goes to the last rank. */
@@ -106,14 +124,18 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
  * "hybrid_min_n", "local_min" / "dense_hint" (routing thresholds of the streaming kernel),
  * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
  * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
- * "zero_copy_max", "stream_copy" (staging copies of pageable arrays with non-temporal stores: 1 [default] / 0).
+ * "zero_copy_max", "stream_copy" (staging copies of pageable arrays with non-temporal stores: 1 [default] / 0),
+ * "min_n", "fallback", "host_threads" (see above).
  * Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
- * Read-only keys for get: "launches" (kernels launched so far), "device_count", "sm_count". */
+ * Read-only keys for get: "launches" (kernels launched so far), "host_core_calls", "fallbacks", "device_count",
+ * "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);
 int fabe13_cuda_get_option(const char* key, long long* value);
 
 int fabe13_cuda_device_count(void);
-int fabe13_cuda_last_error(void);               /* last non-zero cudaError_t seen by this library, 0 if none */
+/* last non-zero cudaError_t this library saw ON THE CALLING THREAD (thread-local: clear / call / check needs no lock;
+ * errors of the library's worker threads are handed to the thread that made the call), 0 if none */
+int fabe13_cuda_last_error(void);
 const char* fabe13_cuda_last_error_string(void);
 void fabe13_cuda_clear_error(void);
 
@@ -123,6 +145,9 @@ void fabe13_debug_host_core(const double* in, double* sin_out, double* cos_out, 
 void fabe13_debug_host_sincosf(const float* in, float* sin_out, float* cos_out, size_t n, int core);
 /* Same for the derived functions: op = 3 (tan), 4 (cot), 5 (sinc). */
 void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, int core);
+/* The host ARRAY loop exactly as the small-n route and the fallback run it (vectorised plain path + patched lanes;
+ * op = 0 for sincos; either output may be NULL), so CPU-only CI can compare it with the per-element routine. */
+void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads);
 
 /* Bench/test hooks: fill a device array with the deterministic synthetic inputs used by bench.py and the parity
  * tests (counter-based splitmix64; the same generator exists on the host in oracle/fabe13_oracle.c).

@@ -291,7 +291,7 @@ def test_host_side_is_clean_under_sanitizers(tmp_path, flavour):
     for f in san:
         cmd += ["-Xcompiler", f]
     cmd += ["-o", exe] + [os.path.join(root, p) for p in ("tools/host_sanitize.cu", "fabe_b200/csrc/fabe13_kernels.cu",
-                                                           "fabe_b200/csrc/fabe13_shim.cu")] + ["-lpthread"]
+                                                           "fabe_b200/csrc/fabe13_shim.cu", "fabe_b200/csrc/fabe13_hostcore.cpp")] + ["-lpthread"]
     build = subprocess.run(cmd, capture_output=True, text=True)
     if build.returncode != 0 and re.search(r"lib(a|t|ub)san", build.stderr + build.stdout):
         pytest.skip("sanitizer runtime not installed")

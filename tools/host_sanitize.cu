@@ -4,7 +4,8 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -cudart static \
 //        -Xcompiler -fsanitize=address,undefined,-fno-sanitize-recover=all,-ffp-contract=off,-mfma \
-//        -o tools/host_sanitize tools/host_sanitize.cu fabe_b200/csrc/fabe13_kernels.cu fabe_b200/csrc/fabe13_shim.cu -lpthread
+//        -o tools/host_sanitize tools/host_sanitize.cu fabe_b200/csrc/fabe13_kernels.cu fabe_b200/csrc/fabe13_shim.cu \
+//        fabe_b200/csrc/fabe13_hostcore.cpp -lpthread
 //   tools/host_sanitize        (exit code 0 and "host_sanitize: ok" = clean)
 // and the same with -Xcompiler -fsanitize=thread instead of address,undefined for the threaded section at the end.
 #include <math.h>
@@ -66,6 +67,63 @@ int main() {
                 if (d[i] == d[i] && fabs(d[i]) < 1e300) acc += d[i];
         }
     }
+    // the host ARRAY loop (small-n route and fallback of the product): odd sizes on exactly-sized arrays, in place,
+    // single outputs, derived functions, several threads -- bit for bit against the per-element routine
+    for (size_t m : {(size_t)1, (size_t)7, (size_t)8, (size_t)127, (size_t)128, (size_t)129, (size_t)1000, (size_t)65537, (size_t)300001}) {
+        const size_t off = (m * 7919) % (n - m);
+        for (int core = 0; core < 2; ++core) {
+            std::vector<double> x(in.begin() + off, in.begin() + off + m), ws(m), wc(m), as(m), ac(m), inplace(x);
+            fabe13_debug_host_core(x.data(), ws.data(), wc.data(), nullptr, m, core);
+            fabe13_debug_host_array(x.data(), as.data(), ac.data(), m, 0, core, 3);
+            fabe13_debug_host_array(inplace.data(), inplace.data(), nullptr, m, 0, core, 1);
+            if (memcmp(ws.data(), as.data(), m * 8) || memcmp(wc.data(), ac.data(), m * 8) || memcmp(ws.data(), inplace.data(), m * 8)) {
+                fprintf(stderr, "host array loop differs from the per-element routine (m=%zu core=%d)\n", m, core);
+                return 1;
+            }
+            fabe13_debug_host_array(x.data(), nullptr, ac.data(), m, 0, core, 2);
+            if (memcmp(wc.data(), ac.data(), m * 8)) return 1;
+            for (int op = 3; op <= 5; ++op) {
+                fabe13_debug_host_derived(x.data(), ws.data(), m, op, core);
+                fabe13_debug_host_array(x.data(), as.data(), nullptr, m, op, core, 2);
+                if (memcmp(ws.data(), as.data(), m * 8)) {
+                    fprintf(stderr, "host array loop, derived op %d differs (m=%zu core=%d)\n", op, m, core);
+                    return 1;
+                }
+            }
+        }
+    }
+    // the C entry points themselves.  Small n stays on the host core whether or not a GPU is visible; on a box without
+    // one, the void entry falls back to the host core for large n too and the int entries report the error.
+    {
+        const size_t m = 5000;
+        std::vector<double> x(in.begin(), in.begin() + m), ws(m), wc(m), as(m), ac(m);
+        fabe13_debug_host_core(x.data(), ws.data(), wc.data(), nullptr, m, 0);
+        fabe13_sincos(x.data(), as.data(), ac.data(), (int)m);
+        if (memcmp(ws.data(), as.data(), m * 8) || memcmp(wc.data(), ac.data(), m * 8)) {
+            fprintf(stderr, "fabe13_sincos (small n) differs from the per-element routine\n");
+            return 1;
+        }
+        if (fabe13_sin_host(x.data(), as.data(), m) != 0 || memcmp(ws.data(), as.data(), m * 8)) return 1;
+        if (fabe13_cos_host(x.data(), ac.data(), m) != 0 || memcmp(wc.data(), ac.data(), m * 8)) return 1;
+        if (fabe13_cuda_device_count() == 0) {
+            const size_t big = 200000;
+            std::vector<double> bx(in.begin(), in.begin() + big), bs(big), bc(big), hs(big), hc(big);
+            fabe13_debug_host_core(bx.data(), hs.data(), hc.data(), nullptr, big, 0);
+            fabe13_cuda_clear_error();
+            fabe13_sincos(bx.data(), bs.data(), bc.data(), (int)big);  // no GPU: host fallback, error recorded
+            if (memcmp(hs.data(), bs.data(), big * 8) || memcmp(hc.data(), bc.data(), big * 8) || fabe13_cuda_last_error() == 0) {
+                fprintf(stderr, "fabe13_sincos fallback without a GPU is broken\n");
+                return 1;
+            }
+            if (fabe13_sincos_host(bx.data(), bs.data(), bc.data(), big) == 0) {
+                fprintf(stderr, "fabe13_sincos_host must report the missing GPU\n");
+                return 1;
+            }
+            fabe13_cuda_clear_error();
+        }
+        (void)fabe13_cuda_trim();
+        (void)fabe13_cuda_shutdown();
+    }
     std::vector<float> fin(n), fs(n), fc(n);
     for (size_t i = 0; i < n; ++i) {
         const uint64_t b = splitmix64(seed);
@@ -108,7 +166,8 @@ int main() {
     // option table: every documented key, out-of-range values, unknown and empty keys
     const char* keys[] = {"core", "unroll", "blocks_per_sm", "tiles_per_block", "small_n", "worklist", "hybrid_min_n", "local_min",
                           "dense_hint", "worklist_shift", "second_pass_blocks_per_sm", "pdl", "chunk_elems", "host_devices",
-                          "stage_threads", "zero_copy_max", "stream_copy", "launches", "no_such_option", ""};
+                          "stage_threads", "zero_copy_max", "stream_copy", "min_n", "fallback", "host_threads", "launches",
+                          "host_core_calls", "fallbacks", "no_such_option", ""};
     for (const char* key : keys) {
         long long v = 0;
         const int rc = fabe13_cuda_get_option(key, &v);
@@ -138,6 +197,9 @@ int main() {
                     (void)fabe13_cuda_set_option("core", rep & 1);
                     long long v = 0;
                     (void)fabe13_cuda_get_option("core", &v);
+                    fabe13_sincos(in.data() + (size_t)w * 4096, ls.data(), lc.data(), 4096);  // small-n route, per thread
+                    fabe13_cuda_clear_error();
+                    (void)fabe13_cuda_last_error();
                     for (int i = 0; i < 256; ++i) {
                         const double y = fabe13_sin(0.001 * i + w);
                         if (y == y) sums[(size_t)w] += y + fabe13_cos(1e300 * (i + 1)) + fabe13_tan(0.5 + i);
