@@ -150,7 +150,7 @@ def test_every_documented_option_exists_and_round_trips(fabe13):
     library knows no option the header does not name."""
     hdr = open(os.path.join(ROOT, "include", "fabe13_cuda.h")).read()
     block = hdr[hdr.index("/* Options:"):hdr.index("int fabe13_cuda_set_option")]
-    named = set(re.findall(r'"([a-z_0-9]+)"', block)) - {"launches", "device_count", "sm_count"}
+    named = set(re.findall(r'"([a-z_0-9]+)"', block)) - {"launches", "device_count", "sm_count", "host_core_calls", "fallbacks"}
     assert len(named) >= 17, named
     for key in sorted(named):
         v = fabe13.get_option(key)          # KeyError = documented but unknown
@@ -201,3 +201,155 @@ def test_python_layer_rejects_outputs_the_library_cannot_check(fabe13):
     api._check_out(tb[5:21], xt, "out")
     api._check_out(xt, xt, "out")
     api._check_out(torch.zeros(16, dtype=torch.float32), torch.zeros(16, dtype=torch.float32), "out", "float32")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def test_small_host_calls_stay_on_the_host_core(fabe13, oracle):
+    """Host-pointer calls below option "min_n" never touch the GPU (reference: n < 32 -> scalar loop,
+    fabe13/fabe13.c:226-229): they work on a box without one, through every host entry point, count as
+    "host_core_calls", launch nothing, and give the bits of the per-element routine the kernels also compile."""
+    lib = fabe13._lib.load()
+    assert fabe13.get_option("min_n") == 8192
+    x = oracle.fill_uniform(8191, 5, -1e6, 1e6)
+    x[:8] = [0.0, -0.0, np.inf, np.nan, 1e300, 2.0**45, 5e-324, -1e-9]
+    hs, hc, _ = fabe13.host_core(x, 0)
+    calls, launches = fabe13.get_option("host_core_calls"), fabe13.get_option("launches")
+    for n in (1, 2, 31, 32, 33, 1000, 8191):
+        s, c = fabe13.sincos(x[:n])
+        assert np.array_equal(bits(s), bits(hs[:n])) and np.array_equal(bits(c), bits(hc[:n])), n
+        s2, c2 = np.empty(n), np.empty(n)
+        fabe13.sincos_legacy(x[:n].copy(), s2, c2)
+        assert np.array_equal(bits(s2), bits(hs[:n])) and np.array_equal(bits(c2), bits(hc[:n])), n
+    assert np.array_equal(bits(fabe13.sin_array(x)), bits(hs)) and np.array_equal(bits(fabe13.cos_array(x)), bits(hc))
+    for op, fn in ((fabe13.OP_TAN, fabe13.tan_array), (fabe13.OP_COT, fabe13.cot_array), (fabe13.OP_SINC, fabe13.sinc_array)):
+        assert np.array_equal(bits(fn(x)), bits(fabe13.host_derived(x, op))), op
+    with np.errstate(over="ignore"):
+        xf = x.astype(np.float32)
+    sf, cf = fabe13.sincosf(xf)
+    wf, vf = fabe13.host_sincosf(xf)
+    assert np.array_equal(sf.view(np.uint32), wf.view(np.uint32)) and np.array_equal(cf.view(np.uint32), vf.view(np.uint32))
+    y = x[:100].copy()                      # in place, as the reference's callers may
+    assert lib.fabe13_sincos_host(y.ctypes.data, y.ctypes.data, np.empty(100).ctypes.data, 100) == 0
+    assert np.array_equal(bits(y), bits(hs[:100]))
+    assert fabe13.get_option("host_core_calls") >= calls + 14 + 6
+    assert fabe13.get_option("launches") == launches
+    assert lib.fabe13_cuda_last_error() == 0
+
+
+def test_void_entry_falls_back_to_the_host_core_when_cuda_fails(fabe13, oracle):
+    """The reference's fabe13_sincos returns void (fabe13/fabe13.h:51-56): when CUDA cannot run the call, the outputs
+    are filled by the host instantiation of the same core and the error stays readable; the int entry points report
+    it instead.  (Runs where no GPU is visible -- the CPU CI box; on a GPU box the failure cannot be provoked.)"""
+    lib = fabe13._lib.load()
+    if lib.fabe13_cuda_device_count() != 0:
+        pytest.skip("a CUDA device is visible: no failure to fall back from")
+    n = 300_001
+    x = oracle.fill_uniform(n, 6, -1e4, 1e4)
+    x[::1000] = oracle.fill_loguniform(len(x[::1000]), 7)
+    hs, hc, _ = fabe13.host_core(x, 0)
+    s, c = np.full(n, 7.0), np.full(n, 7.0)
+    before = fabe13.get_option("fallbacks")
+    lib.fabe13_cuda_clear_error()
+    lib.fabe13_sincos(x.ctypes.data, s.ctypes.data, c.ctypes.data, n)
+    assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
+    assert lib.fabe13_cuda_last_error() != 0 and fabe13.get_option("fallbacks") == before + 1
+    assert lib.fabe13_sincos_host(x.ctypes.data, s.ctypes.data, c.ctypes.data, n) != 0   # error channel: no fallback
+    with pytest.raises(fabe13._lib.Fabe13Error):
+        fabe13.sincos(x)
+    try:
+        fabe13.set_option("fallback", 0)
+        s[:] = 7.0
+        lib.fabe13_sincos(x.ctypes.data, s.ctypes.data, c.ctypes.data, n)
+        assert (s == 7.0).all()             # switched off: outputs untouched, error recorded
+        assert lib.fabe13_cuda_last_error() != 0
+    finally:
+        fabe13.set_option("fallback", 1)
+        lib.fabe13_cuda_clear_error()
+
+
+def test_last_error_is_per_thread(fabe13):
+    import threading
+
+    lib = fabe13._lib.load()
+    lib.fabe13_cuda_clear_error()
+    seen = {}
+
+    def other():
+        lib.fabe13_cuda_clear_error()
+        seen["before"] = lib.fabe13_cuda_last_error()
+        lib.fabe13_sin_device(None, None, 5, None)     # refused: null output
+        seen["after"] = lib.fabe13_cuda_last_error()
+
+    t = threading.Thread(target=other)
+    t.start()
+    t.join()
+    assert seen["before"] == 0 and seen["after"] != 0
+    assert lib.fabe13_cuda_last_error() == 0            # this thread made no failing call
+
+
+def test_pinned_array_views_keep_their_block_alive(fabe13, monkeypatch):
+    """`a = PinnedArray(n).array` (or any slice of it) must stay valid after the wrapper is gone: the block is freed
+    when the last view dies.  Checked with the allocator replaced by malloc/free (no GPU needed)."""
+    import gc
+
+    from fabe_b200 import api
+
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p
+    libc.malloc.argtypes = [ctypes.c_size_t]
+    libc.free.argtypes = [ctypes.c_void_p]
+    freed = []
+
+    class FakeLib:
+        def fabe13_cuda_host_alloc(self, nbytes):
+            return libc.malloc(nbytes)
+
+        def fabe13_cuda_host_free(self, p):
+            freed.append(p)
+            libc.free(p)
+
+    monkeypatch.setattr(api._lib, "load", lambda: FakeLib())
+    a = api.PinnedArray(1000).array
+    a[:] = 3.0
+    tail = a[500:]
+    del a
+    gc.collect()
+    assert not freed and tail[0] == 3.0 and tail.sum() == 1500.0
+    p = api.PinnedArray(10)
+    view = p.array[2:4]
+    p.free()
+    gc.collect()
+    assert not freed
+    del view, tail
+    gc.collect()
+    assert len(freed) == 2
+
+
+def test_reference_example_program_runs_against_the_library():
+    """The reference's own tests/test_fabe13.c (its only consumer besides the benchmark, :99-238), compiled UNMODIFIED
+    against include/fabe13.h and linked with libfabe13.so by `make -C oracle dropin`, run as it is: every printed
+    difference to libm must be at the 1e-16 level (the reference's own build prints 3e-2 for fabe13_sin(1))."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "fabe13_test_runner_b200")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "dropin"], check=True, capture_output=True)
+    if not os.path.exists(exe):
+        pytest.skip("reference sources not mounted and no prebuilt drop-in binary")
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout
+    assert "Active Implementation: CUDA sm_100" in out and "--- Example Complete ---" in out
+    scalar = re.findall(r"fabe13_(sin|cos|sinc):\s*(\S+) \(ref: (\S+), diff: (\S+)\)", out)
+    assert len(scalar) == 60                       # 20 inputs x sin, cos, sinc
+    assert max(float(d) for _, _, _, d in scalar) <= 2.3e-16
+    for fn, got, ref, _ in scalar:
+        assert (got.lstrip("+-") == "nan") == (ref.lstrip("+-") == "nan"), (fn, got, ref)
+    # tan / cot: one division of two 1-ulp values; compare relatively, where libm's own value is finite and moderate
+    for fn, got, ref, _ in re.findall(r"fabe13_(tan|cot):\s*(\S+) \(ref: (\S+), diff: (\S+)\)", out):
+        g, r = float(got), float(ref)
+        if np.isfinite(r) and 1e-3 < abs(r) < 1e3:
+            assert abs(g - r) <= 1e-15 * abs(r), (fn, got, ref)
+    ramp = re.findall(r"in\[(\d+)\]=\S+ -> sin=\S+ \(diff=(\S+)\), cos=\S+ \(diff=(\S+)\)", out)
+    assert [int(i) for i, _, _ in ramp] == [0, 1, 2, 3, 4, 99]
+    assert max(max(float(a), float(b)) for _, a, b in ramp) <= 2.3e-16

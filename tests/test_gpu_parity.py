@@ -43,7 +43,9 @@ def gpu_sincos(fabe13, cuda, x):
 # worklist + second-pass kernel alone (worklist=1), and the hybrid sequence forced at every size (worklist=3).  The
 # heaviest cases run in the default mode only; the tests of the global worklist's own machinery (capacity/overflow
 # rescan, PDL, caller workspace) are skipped where no global worklist exists.
-HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay",
+HEAVY = {"test_c3_1e9_properties", "test_small_n_route_straddles_the_threshold", "test_trim_and_shutdown_give_memory_back",
+         "test_reference_programs_relinked_run_on_the_gpu", "test_partly_registered_arrays_are_staged_not_faulted",
+         "test_concurrent_pinned_callers_share_the_pipeline", "test_sincosf_device_against_libm_rounded_once", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay",
          "test_sincosf_device_matches_host_bit_for_bit", "test_sincosf_host_entries",
          "test_cot_of_tiny_arguments_is_not_mistaken_for_a_parked_argument", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
          "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
@@ -51,7 +53,7 @@ HEAVY = {"test_c3_1e9_properties", "test_tan_cot_sinc_host", "test_cuda_graph_ca
 GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
                "test_host_path_survives_tuning_changes_between_calls"}
 OPTIONS = ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift",
-           "pdl", "worklist", "hybrid_min_n", "local_min", "dense_hint")
+           "pdl", "worklist", "hybrid_min_n", "local_min", "dense_hint", "min_n")
 
 
 @pytest.fixture(autouse=True, params=[0, 1, 3], ids=["auto-worklist", "global-worklist", "hybrid-worklist"])
@@ -63,6 +65,9 @@ def _defaults(request, fabe13):
         pytest.skip("exercises the global worklist's machinery")
     saved = {k: fabe13.get_option(k) for k in OPTIONS}
     fabe13.set_option("worklist", request.param)
+    # these are the tests of the CUDA path: every host-pointer call goes to the GPU, whatever its size (the small-n
+    # host route has its own tests, which set the option back)
+    fabe13.set_option("min_n", 0)
     yield
     for k, v in saved.items():
         fabe13.set_option(k, v)
@@ -602,8 +607,15 @@ def test_tan_cot_sinc_device(fabe13, cuda, oracle, small_n, core):
         assert np.array_equal(bits(y.cpu().numpy()), bits(want[1:])), f"op {op} in place"
     ls, lc = oracle.libm(x)
     body = np.isfinite(x) & (np.abs(x) > 1e-6)
+    # independent truth, applied to the DEVICE results directly: libm's sine and cosine, one division in numpy
+    tol = 1e-15 if core == 0 else 5e-15                                  # psi core: 4.4e-16 per value
     t = fabe13.tan_array(xt).cpu().numpy()
-    assert (np.abs(t[body] - (ls / lc)[body]) / np.abs((ls / lc)[body])).max() < (1e-15 if core == 0 else 5e-15)  # psi core: 4.4e-16 per value
+    assert (np.abs(t[body] - (ls / lc)[body]) / np.abs((ls / lc)[body])).max() < tol
+    ct = fabe13.cot_array(xt).cpu().numpy()
+    assert (np.abs(ct[body] - (lc / ls)[body]) / np.abs((lc / ls)[body])).max() < tol
+    sc = fabe13.sinc_array(xt).cpu().numpy()
+    assert (np.abs(sc[body] - (ls / x)[body]) / np.abs((ls / x)[body])).max() < tol
+    assert (sc[np.abs(x) < 1e-9] == 1.0).all() and np.isnan(ct[x == 0.0]).all() and np.isnan(t[~np.isfinite(x)]).all()
 
 
 @pytest.mark.parametrize("worklist,shift", [(1, 20), (1, 3), (3, 3)])
@@ -985,3 +997,202 @@ def test_graft_entry_smoke(fabe13, cuda):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.smoke()
+
+
+def test_sincosf_device_against_libm_rounded_once(fabe13, cuda):
+    """FP32 entry on the device against independent truth: glibc's double sin/cos of the widened argument, rounded once
+    to float.  Contract (include/fabe13_cuda.h): within 0.5003 ulp, i.e. equal to that value except at near-ties."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    x = np.concatenate([rng.uniform(-1e4, 1e4, 2_000_000), rng.uniform(-1e9, 1e9, 500_000),
+                        np.ldexp(rng.uniform(1, 2, 500_000), rng.integers(-100, 127, 500_000))]).astype(np.float32)
+    s, c = fabe13.sincosf(torch.from_numpy(x).to(cuda))
+    torch.cuda.synchronize()
+    s, c = s.cpu().numpy(), c.cpu().numpy()
+    xd = x.astype(np.float64)
+    for got, truth in ((s, np.sin(xd)), (c, np.cos(xd))):
+        want = truth.astype(np.float32)
+        off = got != want
+        assert off.mean() < 1e-4, off.mean()
+        # where it differs it is the neighbouring float, and the truth lies (almost) half way between the two
+        ulp = np.spacing(np.abs(want[off]).astype(np.float32)).astype(np.float64)
+        assert (np.abs(got[off].astype(np.float64) - truth[off]) <= 0.5003 * ulp).all()
+
+
+def test_small_n_route_straddles_the_threshold(fabe13, cuda, oracle):
+    """Host-pointer calls below "min_n" run on the host core, from "min_n" on they launch kernels -- same bits on both
+    sides of the cut, for pageable and pinned arrays; device pointers go to the GPU whatever their size (reference:
+    SMALL_N_THRESHOLD, fabe13/fabe13.c:73, :226-229)."""
+    import torch
+
+    fabe13.set_option("min_n", 8192)
+    n = 8192
+    x = oracle.fill_uniform(n + 8, 91, -1e5, 1e5)
+    x[::517] = oracle.fill_loguniform(len(x[::517]), 92)
+    x[1], x[2], x[3] = np.nan, 0.0, 1e-300
+    hs, hc, _ = fabe13.host_core(x, 0)
+    px, ps, pc = fabe13.PinnedArray(n + 8), fabe13.PinnedArray(n + 8), fabe13.PinnedArray(n + 8)
+    px.array[:] = x
+    for m, on_gpu in ((n - 1, False), (n, True), (n + 8, True), (100, False)):
+        launches, calls = fabe13.get_option("launches"), fabe13.get_option("host_core_calls")
+        s, c = fabe13.sincos(x[:m].copy())                                       # pageable
+        fabe13.sincos(px.array[:m], out_sin=ps.array[:m], out_cos=pc.array[:m])  # pinned
+        s2, c2 = np.empty(m), np.empty(m)
+        fabe13.sincos_legacy(x[:m].copy(), s2, c2)                               # the reference's own entry
+        assert (fabe13.get_option("launches") > launches) == on_gpu, m
+        assert (fabe13.get_option("host_core_calls") == calls + 3) == (not on_gpu), m
+        for got_s, got_c in ((s, c), (ps.array[:m], pc.array[:m]), (s2, c2)):
+            assert np.array_equal(bits(got_s), bits(hs[:m])) and np.array_equal(bits(got_c), bits(hc[:m])), m
+    launches = fabe13.get_option("launches")
+    xt = torch.from_numpy(x[:10]).to(cuda)
+    st, ct = torch.empty_like(xt), torch.empty_like(xt)
+    fabe13.sincos_legacy(xt, st, ct)                                             # device pointers, n = 10: the GPU
+    assert fabe13.get_option("launches") == launches + 1
+    assert np.array_equal(bits(st.cpu().numpy()), bits(hs[:10]))
+    fabe13.set_option("min_n", 1 << 20)                                          # the cut is an option
+    launches = fabe13.get_option("launches")
+    s, c = fabe13.sincos(x)
+    assert fabe13.get_option("launches") == launches and np.array_equal(bits(s), bits(hs))
+
+
+def test_trim_and_shutdown_give_memory_back(fabe13, cuda, oracle):
+    """fabe13_cuda_trim / _shutdown release the host pipeline's buffers and the pool's cached scratch; the library
+    re-creates what it needs on the next call."""
+    import torch
+
+    lib = fabe13._lib.load()
+    n = 20_000_000
+    x = oracle.fill_uniform(n, 93, -1e4, 1e4)
+    hs, hc, _ = fabe13.host_core(x[:100_000], 0)
+    px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
+    px.array[:] = x
+
+    def run_all():
+        fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)              # pinned pipeline: 8 slots of device buffers
+        assert np.array_equal(bits(ps.array[:100_000]), bits(hs))
+        s, c = fabe13.sincos(x[:3_000_000])                                      # staged pipeline: pinned staging buffers
+        assert np.array_equal(bits(s[:100_000]), bits(hs))
+        s, c = fabe13.sincos(x[:1000])                                           # bounce buffer
+        assert np.array_equal(bits(c), bits(hc[:1000]))
+
+    run_all()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free_busy, _ = torch.cuda.mem_get_info()
+    assert lib.fabe13_cuda_trim() == 0
+    free_trimmed, _ = torch.cuda.mem_get_info()
+    assert free_trimmed - free_busy >= 8 * 3 * (n // 6) * 8 * 0.9, (free_busy, free_trimmed)   # the slots' device buffers are back
+    run_all()
+    assert lib.fabe13_cuda_shutdown() == 0
+    run_all()                                                                    # re-initialises itself
+    assert lib.fabe13_cuda_last_error() == 0
+
+
+def test_partly_registered_arrays_are_staged_not_faulted(fabe13, cuda, oracle):
+    """A pointer into page-locked memory whose range runs past the locked region is treated as pageable (staged), not
+    handed to a zero-copy kernel or a copy engine that would fault on the unlocked tail."""
+    lib = fabe13._lib.load()
+    n = 1 << 20
+    x = oracle.fill_uniform(n, 94, -1e4, 1e4)
+    s, c = np.empty_like(x), np.empty_like(x)
+    hs, hc, _ = fabe13.host_core(x, 0)
+    half = (n // 2) * 8
+    for a in (x, s, c):
+        assert lib.fabe13_cuda_host_register(a.ctypes.data, half) == 0           # the first half only
+    try:
+        fabe13.sincos(x, out_sin=s, out_cos=c)
+        assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc))
+        fabe13.sincos(x[: n // 2], out_sin=s[: n // 2], out_cos=c[: n // 2])      # wholly inside: the pinned route
+        assert np.array_equal(bits(s[: n // 2]), bits(hs[: n // 2]))
+    finally:
+        for a in (x, s, c):
+            assert lib.fabe13_cuda_host_unregister(a.ctypes.data) == 0
+    assert lib.fabe13_cuda_last_error() == 0
+
+
+def test_concurrent_pinned_callers_share_the_pipeline(fabe13, cuda, oracle):
+    """Host-pointer callers on one device no longer serialise behind one lock: their chunks interleave on the slots'
+    streams.  Three threads with different sizes (so the slots are re-sized under them) and a pageable caller."""
+    import threading
+
+    sizes = [30_000_001, 18_000_000, 25_000_003]
+    arrays, want, errors = [], [], []
+    for t, n in enumerate(sizes):
+        px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
+        px.array[:] = oracle.fill_uniform(n, 95 + t, -1e4, 1e4)
+        px.array[5::100_003] = 1e200
+        arrays.append((px, ps, pc))
+        want.append(fabe13.host_core(px.array[-200_000:], 0))
+    xp = oracle.fill_uniform(5_000_000, 99, -1e4, 1e4)
+    wp = fabe13.host_core(xp[:200_000], 0)
+
+    def pinned(t):
+        try:
+            px, ps, pc = arrays[t]
+            for _ in range(3):
+                ps.array[-200_000:] = 0
+                fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)
+                if not (np.array_equal(bits(ps.array[-200_000:]), bits(want[t][0])) and np.array_equal(bits(pc.array[-200_000:]), bits(want[t][1]))):
+                    errors.append(("pinned", t))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    def pageable():
+        try:
+            for _ in range(3):
+                s, c = fabe13.sincos(xp)
+                if not np.array_equal(bits(s[:200_000]), bits(wp[0])):
+                    errors.append(("pageable",))
+        except Exception as e:  # noqa: BLE001
+            errors.append(("pageable", repr(e)))
+
+    threads = [threading.Thread(target=pinned, args=(t,)) for t in range(3)] + [threading.Thread(target=pageable)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
+def test_reference_programs_relinked_run_on_the_gpu(fabe13, cuda):
+    """The reference's own consumers, compiled unmodified against include/fabe13.h and linked with libfabe13.so
+    (`make -C oracle dropin`; binaries travel with the snapshot): tests/test_fabe13.c is run as it is, and
+    benchmark_fabe13.c until its N = 1e6 row (it has no size argument; rows beyond cost minutes and 37 GB).  Asserted:
+    the library they report, the accuracy lines they print (reference/fabe13/benchmark_fabe13.c:279-296,
+    tests/test_fabe13.c:217-238), and that the rows the GPU serves were served by the GPU."""
+    import os
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runner = os.path.join(root, "oracle", "_ref", "fabe13_test_runner_b200")
+    bench = os.path.join(root, "oracle", "_ref", "fabe13_benchmark_b200")
+    if not (os.path.exists(runner) and os.path.exists(bench)):
+        pytest.skip("drop-in binaries were not built (reference sources not mounted at build time)")
+    out = subprocess.run([runner], check=True, capture_output=True, text=True, timeout=120).stdout
+    assert re.search(r"Active Implementation: CUDA sm_100 \(NVIDIA B200", out) and "--- Example Complete ---" in out
+    diffs = [float(d) for d in re.findall(r"fabe13_(?:sin|cos|sinc):\s*\S+ \(ref: \S+, diff: (\S+)\)", out)]
+    assert len(diffs) == 60 and max(diffs) <= 2.3e-16
+    ramp = re.findall(r"in\[\d+\]=\S+ -> sin=\S+ \(diff=(\S+)\), cos=\S+ \(diff=(\S+)\)", out)
+    assert len(ramp) == 6 and max(max(float(a), float(b)) for a, b in ramp) <= 2.3e-16
+    # the benchmark: line-buffered, stopped once the 1e6 row and its accuracy line are out
+    proc = subprocess.Popen(["stdbuf", "-oL", bench], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    lines = []
+    try:
+        for line in proc.stdout:
+            lines.append(line)
+            if "on 1000000 samples" in line:
+                break
+    finally:
+        proc.kill()
+        proc.wait()
+    text = "".join(lines)
+    assert "FABE13 Active Implementation: CUDA sm_100 (NVIDIA B200" in text
+    acc = re.findall(r"Max diff vs libm \(on (\d+) samples\): sin=(\S+), cos=(\S+)", text)
+    assert [int(a[0]) for a in acc] == [10, 100, 1000, 10_000, 100_000, 1_000_000]
+    assert max(max(float(a[1]), float(a[2])) for a in acc) <= 2.3e-16      # reference README: 1.224e-11 on this range
+    rows = re.findall(r"^(\d+)\s+\|\s+(\S+)\s+\|\s+(\S+)\s+\|\s+(\S+)\s+\|", text, flags=re.M)
+    assert [int(r[0]) for r in rows] == [10, 100, 1000, 10_000, 100_000, 1_000_000]
+    mops = {int(r[0]): float(r[3]) for r in rows}
+    assert mops[10] >= 20 and mops[100] >= 100 and mops[1000] >= 150, mops   # small rows: the host core, no launch per call
