@@ -9,13 +9,19 @@
 Workload (default c3 = BASELINE configs[2]): N = 1e9 doubles uniform in [-1e4, 1e4], synthetic (counter-based
 generator, same bits on host and device), slice-sharded contiguously over the ranks: total work is fixed, so
 "scaling" is "strong".  A step = one pass of the hot path (fabe13_sincos_device on the rank's slice).
-  value      whole-job Gelem/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
-  e2e        the same metric through the host-pointer C-ABI entry (fabe13_sincos_host) with pinned HOST buffers:
-             H2D of the inputs and D2H of both outputs inside the timed region
-  roofline   24 algorithmic bytes per element / the measured step time, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference library (oracle/_ref, its build.sh flags) on the host cores, bounded sample
+  value         whole-job Gelem/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
+  roofline      24 algorithmic bytes per element / the measured step time, against MEASURED_PEAKS.json hbm_gbs;
+                .sustained = the same over >= 2 s of back-to-back steps after the timed region (power-capped clocks)
+  e2e           the same metric through the host-pointer C-ABI entry (fabe13_sincos_host) with pinned HOST buffers, the
+                rank's whole slice: H2D of the inputs and D2H of both outputs inside the timed region;
+                .roofline = a bare cudaMemcpyAsync H2D || D2H probe in the path's 8:16 byte mix, run on the same
+                buffers by all ranks at once right before it -- what the host link gives at this GPU count
+  e2e_pageable  what an unmodified caller of the reference gets: malloc'd (numpy) arrays through void fabe13_sincos()
+  cpu_baseline  the reference library (oracle/_ref, built by its own build.sh) on the host cores, bounded sample
+The multi-rank harness (barrier, max over ranks) runs on gloo: the data path has no collective and no NCCL.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -37,6 +43,7 @@ WORKLOADS = {
 BYTES_PER_ELEM = 24  # 8 B read + 8 B sin + 8 B cos
 METRIC = "fp64_sincos_throughput"
 UNIT = "Gelem/s"
+KERNEL_SOURCES = ("fabe13_kernels.cu", "fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h")
 
 
 def log(*a):
@@ -47,8 +54,8 @@ _REAL_STDOUT = None
 
 
 def claim_stdout():
-    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so move
-    fd 1 to stderr for the whole run and keep the original for emit()."""
+    """The contract is ONE JSON line on stdout.  Libraries print there too, so move fd 1 to stderr for the whole run
+    and keep the original for emit()."""
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
         sys.stdout.flush()
@@ -65,6 +72,14 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def workload_config(workload, n_total):
+    """The part of `config` that names the workload: identical in both arms (the CUDA arm and --impl reference)."""
+    desc, _, gen, gargs, seed = WORKLOADS[workload]
+    return {"workload": desc, "elements_total": n_total, "generator": f"{gen}, counter-based splitmix64, seed {seed:#x}",
+            "l2": "every step reads and writes the whole array (24 B/element: 24 GB at N=1e9; per GPU >= 3 GB at 8 GPUs), "
+                  "far beyond the 126 MB L2 and the host's last-level cache; no flush needed"}
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -74,15 +89,29 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_hash():
+    """sha256 over the sources the kernels are compiled from: what an ncu capture has to have been taken on."""
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "fabe_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def ncu_traffic_per_elem():
-    """dram bytes per element of the streaming kernel from the committed ncu capture, if any."""
+    """(dram bytes per element of the streaming kernel, note) from the committed ncu capture -- only if that capture
+    was taken on the kernel sources this run is built from."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             j = json.load(f)
-        return float(j["dram_bytes_per_elem"])
     except Exception:
-        return None
+        return None, "no ncu capture committed (profiles/ncu_traffic.json)"
+    now = kernel_source_hash()
+    if j.get("kernel_source_sha256") != now:
+        return None, (f"the committed ncu capture ({j.get('report')}) was taken on kernel sources "
+                      f"{str(j.get('kernel_source_sha256'))[:12]}, this build is {now[:12]}: not carried over")
+    return float(j["dram_bytes_per_elem"]), f"ncu --set full capture {j.get('report')} on kernel sources {now[:12]}"
 
 
 class ClockSampler:
@@ -136,6 +165,7 @@ class ClockSampler:
         if self.nv:
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
+        return self
 
     def stop(self):
         if self._thread:
@@ -161,16 +191,10 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def sample_per_thread(threads):
-    """Bounded CPU sample: 20M elements per thread (480 MB of arrays, far beyond the CPU caches), capped so that
-    the whole sample stays under 640M elements (15 GB) on hosts with very many cores."""
-    return max(2_000_000, min(20_000_000, 640_000_000 // max(threads, 1)))
-
-
-def make_cpu_runner(workload, per_thread_elems, threads):
-    """Returns (run_once, total_elems, description).  run_once() evaluates the reference's fabe13_sincos on
-    `threads` disjoint slices concurrently (the library itself is single-threaded: one call per slice) and returns
-    the wall time."""
+def make_cpu_runner(workload, total_elems, threads):
+    """Returns (run_once, total_elems, info).  run_once() evaluates the reference's fabe13_sincos on `threads`
+    disjoint contiguous slices of one `total_elems`-element array concurrently (the library itself is single-threaded:
+    one call per slice) and returns the wall time."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
 
@@ -182,39 +206,50 @@ def make_cpu_runner(workload, per_thread_elems, threads):
         ref = Reference(path=path)
         kind = "reference"
         call = lambda x, s, c: ref.sincos_raw(x, s, c)
-        name = f"{os.path.basename(path)} [{ref.name}]"
+        how = ("built by the reference's own build.sh in a scratch copy" if path.endswith("_own.so") else
+               "the reference source compiled with build.sh's flags (oracle/Makefile)")
+        name = f"{os.path.basename(path)} [{ref.name}], {how}"
     else:  # the compiled reference did not travel: fall back to the restated port, and say so
         orc = Oracle()
         kind = "port"
         call = lambda x, s, c: orc.lib.fabe13_oracle_sincos(x.ctypes.data, s.ctypes.data, c.ctypes.data, None, x.size)
         name = "oracle/fabe13_oracle.c (scalar port)"
     o = Oracle()
-    n = per_thread_elems
-    xs, ss, cs = [], [], []
-    for t in range(threads):
-        if gen == "uniform":
-            xs.append(o.fill_uniform(n, seed, args[0], args[1], first_index=t * n))
-        else:
-            xs.append(o.fill_loguniform(n, seed, first_index=t * n))
-        ss.append(np.zeros(n))  # touched: no first-touch page faults inside the timed region
-        cs.append(np.zeros(n))
+    per = (total_elems // threads) & ~7  # slices of whole SIMD vectors (the reference's tails take its scalar core)
+    bounds = [(t * per, (t + 1) * per if t < threads - 1 else total_elems) for t in range(threads)]
+    x = np.empty(total_elems)
+    s = np.empty(total_elems)
+    c = np.empty(total_elems)
     pool = ThreadPoolExecutor(max_workers=threads)
+
+    def fill(t):
+        b, e = bounds[t]
+        if gen == "uniform":
+            o.lib.fabe13_oracle_fill_uniform(x[b:e].ctypes.data, e - b, seed, b, args[0], args[1])
+        else:
+            o.lib.fabe13_oracle_fill_loguniform(x[b:e].ctypes.data, e - b, seed, b)
+        s[b:e] = 0.0  # touched by the thread that will write them: no first-touch page faults inside the timed region
+        c[b:e] = 0.0
+
+    list(pool.map(fill, range(threads)))
 
     def run_once():
         t0 = time.perf_counter()
-        list(pool.map(lambda t: call(xs[t], ss[t], cs[t]), range(threads)))  # ctypes releases the GIL
+        list(pool.map(lambda t: call(x[bounds[t][0]:bounds[t][1]], s[bounds[t][0]:bounds[t][1]], c[bounds[t][0]:bounds[t][1]]),
+                      range(threads)))  # ctypes releases the GIL
         return time.perf_counter() - t0
 
     info = {"kind": kind, "cores": threads, "library": name, "cpu": cpu_model(),
-            "sample": f"{threads} threads x {n} elements of workload {workload} (warm arrays, one fabe13_sincos call per thread)"}
-    return run_once, n * threads, info
+            "sample": f"{total_elems} elements of workload {workload} in {threads} contiguous slices, one fabe13_sincos call per "
+                      f"host thread (the library is single-threaded), warm arrays"}
+    return run_once, total_elems, info
 
 
 def cpu_baseline(workload, seconds_budget=20.0):
     """Bounded CPU sample for the main JSON line: all host threads, and 1 thread (the reference as shipped)."""
     threads = host_threads()
-    per = sample_per_thread(threads)
-    run_all, total, info = make_cpu_runner(workload, per, threads)
+    total = max(2_000_000, min(20_000_000, 640_000_000 // max(threads, 1))) * threads
+    run_all, total, info = make_cpu_runner(workload, total, threads)
     run_all()  # warm-up
     reps, best = 0, float("inf")
     t_start = time.perf_counter()
@@ -224,11 +259,10 @@ def cpu_baseline(workload, seconds_budget=20.0):
         reps += 1
         if time.perf_counter() - t_start > seconds_budget:
             break
-    out_reps = reps
     out = dict(info)
     out["value"] = total / best / 1e9
     out["unit"] = UNIT
-    out["sample"] += f", best of {out_reps} repetitions"
+    out["sample"] += f", best of {reps} repetitions"
     run_one, total1, _ = make_cpu_runner(workload, 20_000_000, 1)
     run_one()
     best1 = min(run_one() for _ in range(3))
@@ -241,8 +275,12 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    per = sample_per_thread(threads)
-    run_once, total, info = make_cpu_runner(args.workload, per, threads)
+    n_total = args.elems or WORKLOADS[args.workload][1]
+    try:
+        run_once, total, info = make_cpu_runner(args.workload, n_total, threads)
+    except MemoryError:  # a host too small for 24 B x N: say so and time a quarter of the array
+        log("bench.py: not enough host memory for the whole workload, timing a quarter of it")
+        run_once, total, info = make_cpu_runner(args.workload, n_total // 4, threads)
     for _ in range(max(args.warmup, 1)):
         run_once()
     times = [run_once() for _ in range(args.steps)]
@@ -251,11 +289,13 @@ def run_reference_arm(args):
     info = dict(info)
     info["value"] = value
     info["unit"] = UNIT
+    config = workload_config(args.workload, n_total)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][0], "sample_elems_per_step": total, "host_threads": threads},
+        "config": config,
+        "setup": {"elements_per_step": total, "host_threads": threads, "step_ms_min": min(times) * 1e3},
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -264,9 +304,52 @@ def run_reference_arm(args):
     return 0
 
 
-def run_e2e(fb, torch, args, x, s, n_local, world, barrier, max_over_ranks):
-    """End to end through the host-pointer entry: pinned host buffers, H2D + D2H inside the timed region."""
-    n_e2e = min(n_local, args.e2e_elems)
+# --------------------------------------------------------------------------------------------------------------
+# end to end: host buffers through the C ABI
+# --------------------------------------------------------------------------------------------------------------
+def link_probe(torch, dev, hx, hs, hc, x, s, c, n, seconds, barrier, max_over_ranks, sum_over_ranks, solo):
+    """Bare copies in the path's mix -- 8 B in : 16 B out per element, chunked as the pipeline chunks them, no kernel --
+    between the very buffers the end-to-end leg uses.  All ranks run inside one window (`solo`: rank 0 alone), so the
+    result is what the host side gives this many GPUs at once.  Returns aggregate (H2D GB/s, D2H GB/s)."""
+    chunk = 4 << 20  # elements: the pipeline's chunk (32 MB in, 2 x 32 MB out)
+    rank = int(os.environ.get("RANK", "0"))
+    active = (not solo) or rank == 0
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    thx, ths, thc = (torch.from_numpy(a) for a in (hx, hs, hc))
+    nchunks = max(1, n // chunk)
+    barrier()
+    t0 = time.perf_counter()
+    moved_in = moved_out = 0
+    i = 0
+    if active:
+        while time.perf_counter() - t0 < seconds:
+            b = (i % nchunks) * chunk
+            e = min(b + chunk, n)
+            with torch.cuda.stream(s_in):
+                x[b:e].copy_(thx[b:e], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                ths[b:e].copy_(s[b:e], non_blocking=True)
+                thc[b:e].copy_(c[b:e], non_blocking=True)
+            moved_in += 8 * (e - b)
+            moved_out += 16 * (e - b)
+            i += 1
+            if i % 8 == 0:  # keep a bounded number of copies queued
+                s_in.synchronize()
+                s_out.synchronize()
+        s_in.synchronize()
+        s_out.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    tot_in, tot_out = sum_over_ranks(float(moved_in)), sum_over_ranks(float(moved_out))
+    barrier()
+    return tot_in / dt / 1e9, tot_out / dt / 1e9
+
+
+def run_e2e(fb, torch, args, dev, x, s, c, n_local, world, barrier, max_over_ranks, sum_over_ranks):
+    """End to end through the host-pointer entry: pinned host buffers, H2D + D2H inside the timed region; then the
+    same with pageable arrays through the reference's own void entry."""
+    import numpy as np
+
+    n_e2e = min(n_local, args.e2e_elems) if args.e2e_elems else n_local
     # every rank must end up with the same sample size (the timed loop contains a collective): agree on success
     bufs = None
     for _ in range(4):
@@ -277,36 +360,82 @@ def run_e2e(fb, torch, args, x, s, n_local, world, barrier, max_over_ranks):
             bufs, ok = None, 0.0
         if max_over_ranks(-ok) == -1.0:  # min over ranks of ok
             break
-        if bufs:
-            for p in bufs:
-                p.free()
         bufs = None
         n_e2e //= 4
         log(f"bench.py: pinned allocation failed on some rank, retrying the end-to-end leg with {n_e2e} elements")
     if bufs is None:
-        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "error": "could not allocate pinned host buffers for the end-to-end leg"}
-    hx, hs, hc = bufs
-    hx.array[:] = x[:n_e2e].cpu().numpy()
+        err = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "error": "could not allocate pinned host buffers for the end-to-end leg"}
+        return err, None
+    hx, hs, hc = (p.array for p in bufs)
+    torch.from_numpy(hx).copy_(x[:n_e2e])
+    first = s[:1000].cpu().numpy()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    fb.sincos(hx.array, out_sin=hs.array, out_cos=hc.array)  # warm-up: allocates the pipeline slots
+    fb.sincos(hx, out_sin=hs, out_cos=hc)  # warm-up: allocates the pipeline slots
+    # the ceiling first: what the link (one GPU) and the host side (all GPUs at once) carry for this mix
+    solo = link_probe(torch, dev, hx, hs, hc, x, s, c, n_e2e, 0.5, barrier, max_over_ranks, sum_over_ranks, True) if world > 1 else None
+    both = link_probe(torch, dev, hx, hs, hc, x, s, c, n_e2e, 1.0, barrier, max_over_ranks, sum_over_ranks, False)
+    hs[:1000] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        fb.sincos(hx.array, out_sin=hs.array, out_cos=hc.array)
+        fb.sincos(hx, out_sin=hs, out_cos=hc)
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = n_e2e * world * e2e_steps / t_e2e / 1e9
-    if float(abs(hs.array[:1000] - s[:1000].cpu().numpy()).max()) != 0.0:
+    if float(abs(hs[:1000] - first).max()) != 0.0:
         raise SystemExit("bench.py: host-path results differ from the device-path results")
-    for p in (hx, hs, hc):
+    peak_gelems = min(both[0] / 8, both[1] / 16)
+    per_gpu = (both[0] + both[1]) / world
+    if solo is None or per_gpu >= 0.9 * (solo[0] + solo[1]):
+        bound = "pcie"
+        why = "every GPU's copies run at the rate one GPU's link carries alone"
+    else:
+        bound = "host_dram"
+        why = (f"{world} GPUs copying at once get {per_gpu:.1f} GB/s each where one alone gets {solo[0] + solo[1]:.1f}: the host side "
+               f"(memory / IOMMU of this VM) is shared")
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_e2e, "d2h_bytes_per_step": 16 * n_e2e,
+           "elements_per_gpu": n_e2e, "steps": e2e_steps,
+           "path": "fabe13_sincos_host, pinned host buffers, " + ("chunked H2D|kernel|D2H copy-engine pipeline"
+                                                                  if n_e2e > fb.get_option("zero_copy_max") else
+                                                                  "zero-copy kernels over PCIe"),
+           "roofline": {"bound": bound, "unit": "GB/s", "peak_gbs": both[0] + both[1], "peak_h2d_gbs": both[0], "peak_d2h_gbs": both[1],
+                        "achieved_gbs": BYTES_PER_ELEM * e2e_value, "peak": peak_gelems, "frac": e2e_value / peak_gelems,
+                        "one_gpu_alone_gbs": (solo[0] + solo[1]) if solo else None,
+                        "how": "bare cudaMemcpyAsync H2D || D2H (8 B : 16 B per element, 32 MB copies, no kernel) on the same pinned "
+                               "buffers, all ranks inside one window, measured in this run right before the timed calls; " + why}}
+    if n_e2e < n_local:
+        e2e["cap"] = f"{n_e2e} of the rank's {n_local} elements (--e2e-elems, or pinned memory did not allow more)"
+    del hx, hs, hc
+    for p in bufs:
         p.free()
-    return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_e2e, "d2h_bytes_per_step": 16 * n_e2e,
-            "elements_per_gpu": n_e2e, "steps": e2e_steps,
-            "path": "fabe13_sincos_host, pinned host buffers, " + ("chunked H2D|kernel|D2H copy-engine pipeline"
-                                                                   if n_e2e > fb.get_option("zero_copy_max") else
-                                                                   "zero-copy kernels over PCIe")}
+    bufs = None
+
+    # what an unmodified caller of the reference passes: pageable arrays, the void entry
+    n_pg = min(n_local, args.pageable_elems) if args.pageable_elems else n_local
+    try:
+        px = np.empty(n_pg)
+        torch.from_numpy(px).copy_(x[:n_pg])
+        ps, pc = np.zeros(n_pg), np.zeros(n_pg)  # touched: no first-touch page faults inside the timed region
+    except MemoryError:
+        return e2e, {"value": None, "unit": UNIT, "error": "not enough host memory for pageable arrays"}
+    fb.sincos_legacy(px, ps, pc)  # warm-up: allocates the staging buffers
+    pg_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(pg_steps):
+        fb.sincos_legacy(px, ps, pc)
+    t_pg = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    if float(abs(ps[:1000] - first).max()) != 0.0:
+        raise SystemExit("bench.py: pageable host-path results differ from the device-path results")
+    pageable = {"value": n_pg * world * pg_steps / t_pg / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * n_pg, "d2h_bytes_per_step": 16 * n_pg,
+                "elements_per_gpu": n_pg, "steps": pg_steps,
+                "path": "void fabe13_sincos(in, sin_out, cos_out, int n) on malloc'd (numpy) arrays: staged through pinned buffers by "
+                        "worker threads (host-memory bound), as a relinked caller of the reference gets it",
+                "stage_threads": fb.get_option("stage_threads") or "auto (3/4 of the hardware threads, at most 16)"}
+    return e2e, pageable
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -321,24 +450,28 @@ def run_cuda_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
+    if not torch.cuda.is_available() or fb.get_option("device_count") == 0:
+        raise SystemExit("bench.py: no CUDA device -- this arm measures the CUDA path and nothing else")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)  # harness barrier / max-over-ranks only: no data-path collective
+        # harness only (barrier, max over ranks) and on gloo: the data path has no collective, NCCL is not initialised
+        dist.init_process_group("gloo")
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(v):
+    def reduce(v, op):
         if world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=op)
         return t.item()
+
+    max_over_ranks = lambda v: reduce(v, dist.ReduceOp.MAX)
+    sum_over_ranks = lambda v: reduce(v, dist.ReduceOp.SUM)
 
     if args.core is not None:
         fb.set_option("core", args.core)
@@ -360,9 +493,7 @@ def run_cuda_arm(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    sampler = ClockSampler(local).start() if rank == 0 else None
     launches0 = fb.get_option("launches")
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -384,34 +515,62 @@ def run_cuda_arm(args):
     if not ident <= 1e-15:
         raise SystemExit(f"bench.py: sin^2+cos^2-1 = {ident} on the timed outputs")
 
-    e2e = None
+    # sustained: the same step back to back for >= sustain_seconds on every rank at once (the 1 kW power cap pulls the
+    # SM clock down after about a second; the burst figure above does not see that)
+    sustained = None
+    if args.sustain_seconds > 0:
+        per_step = max(total_ms / args.steps * 1e-3, 1e-5)
+        k = max(10, int(args.sustain_seconds / per_step) + 1)
+        barrier()
+        sus_sampler = ClockSampler(local).start() if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        barrier()
+        sus_ms = e0.elapsed_time(e1)
+        sus_clocks = sus_sampler.stop() if sus_sampler else None
+        sus_ms_max = max_over_ranks(sus_ms)
+        sustained = (k, sus_ms, sus_ms_max, sus_clocks)
+
+    e2e, pageable = None, None
     if not args.no_e2e:
-        e2e = run_e2e(fb, torch, args, x, s, n_local, world, barrier, max_over_ranks)
+        e2e, pageable = run_e2e(fb, torch, args, dev, x, s, c, n_local, world, barrier, max_over_ranks, sum_over_ranks)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         avg_ms = sum(step_ms) / len(step_ms)
         achieved = BYTES_PER_ELEM * n_local / (avg_ms * 1e-3) / 1e9
-        tpe = ncu_traffic_per_elem()
+        tpe, traffic_note = ncu_traffic_per_elem()
+        config = workload_config(args.workload, n_total)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": (tpe * n_local) if tpe else None, "traffic_source": traffic_note,
+                    "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0,
+                    "algorithmic_bytes_per_launch": BYTES_PER_ELEM * n_local,
+                    "step_ms_avg": avg_ms, "step_ms_median": sorted(step_ms)[len(step_ms) // 2], "step_ms_min": min(step_ms),
+                    "note": "duration = CUDA events around one step on the launching stream: one launch of the fused streaming kernel, rank 0"}
+        if sustained:
+            k, sus_ms, sus_ms_max, sus_clocks = sustained
+            sus_achieved = BYTES_PER_ELEM * n_local * k / (sus_ms * 1e-3) / 1e9
+            roofline["sustained"] = {"seconds": sus_ms * 1e-3, "steps": k, "value": n_total * k / (sus_ms_max * 1e-3) / 1e9, "unit": UNIT,
+                                     "achieved": sus_achieved, "frac": sus_achieved / peak, "frac_of_nominal_8TBps": sus_achieved / 8000.0,
+                                     "clocks": sus_clocks,
+                                     "note": "back-to-back steps right after the timed region, all ranks at once; value = whole job, "
+                                             "achieved/frac = rank 0's GPU"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "elements_total": n_total, "elements_per_gpu": n_local,
-                       "sharding": f"contiguous slices, {world} rank(s), no collective",
-                       "core": ["poly", "psi"][fb.get_option("core")], "unroll": fb.get_option("unroll"),
-                       "blocks_per_sm": fb.get_option("blocks_per_sm"), "worklist": fb.get_option("worklist"),
-                       "l2": "inputs+outputs per GPU (%.1f GB) far exceed the 126 MB L2; no flush needed" % (BYTES_PER_ELEM * n_local / 1e9),
-                       "implementation": fb.implementation_name()},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (tpe * n_local) if tpe else None,
-                         "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "algorithmic_bytes_per_launch": BYTES_PER_ELEM * n_local,
-                         "step_ms_avg": avg_ms, "step_ms_median": sorted(step_ms)[len(step_ms) // 2], "step_ms_min": min(step_ms),
-                         "note": "duration = CUDA events around one step on the launching stream (the fused streaming kernel; "
-                                 "from 2^26 elements per rank on also the counter reset and the second-pass launch, "
-                                 "empty for this workload), rank 0"},
+            "config": config,
+            "setup": {"elements_per_gpu": n_local, "sharding": f"contiguous slices, {world} rank(s), no collective on the data path "
+                                                                "(harness barrier on gloo; NCCL not initialised)",
+                      "core": ["poly", "psi"][fb.get_option("core")], "unroll": fb.get_option("unroll"),
+                      "blocks_per_sm": fb.get_option("blocks_per_sm"), "worklist": fb.get_option("worklist"),
+                      "hybrid_min_n": fb.get_option("hybrid_min_n"), "implementation": fb.implementation_name()},
+            "roofline": roofline,
             "e2e": e2e,
+            "e2e_pageable": pageable,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -422,6 +581,7 @@ def run_cuda_arm(args):
                 line["cpu_baseline"] = {"error": repr(ex)}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -435,10 +595,12 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--elems", type=int, default=0, help="override the total element count")
     ap.add_argument("--core", type=int, default=None, choices=[0, 1])
-    ap.add_argument("--e2e-elems", type=int, default=250_000_000, help="per-GPU element cap of the end-to-end leg")
+    ap.add_argument("--e2e-elems", type=int, default=0, help="per-GPU element cap of the end-to-end leg (0 = the rank's whole slice)")
+    ap.add_argument("--pageable-elems", type=int, default=0, help="per-GPU element cap of the pageable end-to-end leg (0 = whole slice)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the sustained run after the timed region (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiling runs only)")
     args = ap.parse_args()
     claim_stdout()
     if args.warmup < 3 and args.impl == "cuda":

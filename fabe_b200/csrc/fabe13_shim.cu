@@ -68,7 +68,11 @@ struct Config {
     std::atomic<long long> stage_threads{0};  // 0 = auto: min(kSlots, 3/4 of the hardware threads)
     std::atomic<long long> zero_copy_max{(long long)1 << 24};
     std::atomic<long long> stream_copy{1};  // staging copies of the pageable path with non-temporal stores
-    std::atomic<long long> min_n{8192};     // host-pointer calls below this many elements stay on the host core
+    // host-pointer calls below these many elements stay on the host core: measured crossovers (profiles/r02_abi_latency.txt)
+    // of one host thread against the zero-copy kernel (page-locked arrays: 20 us either way at 16k elements) and
+    // against the staged path (pageable arrays: bounce copies + PCIe round trip, 180 vs 290 us at 128k elements)
+    std::atomic<long long> min_n{16384};
+    std::atomic<long long> min_n_pageable{131072};
     std::atomic<long long> fallback{1};     // void fabe13_sincos(): on a CUDA failure fill the outputs on the host core
     std::atomic<long long> host_threads{0}; // threads of that fallback (0 = auto: the hardware threads, at most 16)
 };
@@ -107,6 +111,7 @@ const OptionDesc kOptions[] = {
     {"zero_copy_max", "FABE13_CUDA_ZERO_COPY_MAX", &Config::zero_copy_max, 0, (long long)1 << 30},
     {"stream_copy", "FABE13_CUDA_STREAM_COPY", &Config::stream_copy, 0, 1},
     {"min_n", "FABE13_CUDA_MIN_N", &Config::min_n, 0, (long long)1 << 31},
+    {"min_n_pageable", "FABE13_CUDA_MIN_N_PAGEABLE", &Config::min_n_pageable, 0, (long long)1 << 31},
     {"fallback", "FABE13_CUDA_FALLBACK", &Config::fallback, 0, 1},
     {"host_threads", "FABE13_CUDA_HOST_THREADS", &Config::host_threads, 0, 256},
 };
@@ -727,6 +732,12 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
         return 0;
     }
     const bool pinned = (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED);
+    if (!pinned && n < (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) {
+        // pageable arrays pay two extra host copies and a PCIe round trip: one host thread is faster up to here
+        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), 1);
+        g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     int cur = 0;
     FABE13_TRY(cudaGetDevice(&cur));
     const int ndev_avail = device_count();
@@ -795,9 +806,15 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
         FABE13_TRY(cudaStreamSynchronize(nullptr));
         return 0;
     }
+    const bool pinned = (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED);
+    if (!pinned && n < (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) {
+        fabe13::host_sincosf_array(in, sin_out, cos_out, n, (int)g_cfg.core.load(), 1);
+        g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     DeviceState* ds;
     if (int rc = current_device_state(&ds)) return rc;
-    if (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED) {
+    if (pinned) {
         void *d_in = nullptr, *d_s = nullptr, *d_c = nullptr;
         if (cudaHostGetDevicePointer(&d_in, (void*)in, 0) == cudaSuccess && cudaHostGetDevicePointer(&d_s, sin_out, 0) == cudaSuccess &&
             cudaHostGetDevicePointer(&d_c, cos_out, 0) == cudaSuccess) {

@@ -84,11 +84,13 @@ int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in,
  * one per GPU. */
 int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n);
 
-/* Which host-pointer calls run where.  Below option "min_n" elements (default 8192; FABE13_CUDA_MIN_N) a host-pointer
- * call -- fabe13_sincos and every *_host entry -- is evaluated on the calling thread by the HOST instantiation of the same
- * per-element core the kernels compile for the device (bit-identical results), because a kernel launch plus a
- * synchronisation costs ~13 us and the host core ~2 ns per element.  This mirrors the reference's own small-n route
- * (fabe13/fabe13.c:226-229: n < 32 -> scalar loop).  "min_n" = 0 sends every call to the GPU.
+/* Which host-pointer calls run where.  Below option "min_n" elements (default 16384; FABE13_CUDA_MIN_N) -- below
+ * "min_n_pageable" (default 131072) if any of the arrays is pageable memory -- a host-pointer call (fabe13_sincos and
+ * every *_host entry) is evaluated on the calling thread by the HOST instantiation of the same per-element core the
+ * kernels compile for the device (bit-identical results): a kernel launch plus a synchronisation costs ~13 us, the
+ * host core ~1.3 ns per element, and pageable arrays pay two more host copies and a PCIe round trip on top.  Both
+ * defaults are measured crossovers (profiles/r02_abi_latency.txt).  This mirrors the reference's own small-n route
+ * (fabe13/fabe13.c:226-229: n < 32 -> scalar loop).  Setting both to 0 sends every call to the GPU.
  * On a CUDA failure every int entry point returns the cudaError_t and leaves the outputs unspecified; the void
  * fabe13_sincos(), which has no error channel (fabe13/fabe13.h:51-56), then fills sin_out / cos_out on the host core
  * (option "fallback" = 1, the default; "host_threads" threads) and the error stays readable through
@@ -125,7 +127,7 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
  * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
  * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
  * "zero_copy_max", "stream_copy" (staging copies of pageable arrays with non-temporal stores: 1 [default] / 0),
- * "min_n", "fallback", "host_threads" (see above).
+ * "min_n", "min_n_pageable", "fallback", "host_threads" (see above).
  * Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
  * Read-only keys for get: "launches" (kernels launched so far), "host_core_calls", "fallbacks", "device_count",
  * "sm_count". */

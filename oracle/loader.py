@@ -109,7 +109,8 @@ def ref_variant(kind):
             with open(host) as f:
                 built_on = set(f.read().split())
             if built_on and built_on <= flags:  # -march=native code only where every ISA extension exists
-                order.append("native")
+                order.append("own")     # built by the reference's own build.sh (oracle/build_ref_with_buildsh.sh)
+                order.append("native")  # same flags, compiled directly by oracle/Makefile
     if {"avx512f", "avx512dq"} <= flags:
         order.append("avx512")
     if {"avx2", "fma"} <= flags:

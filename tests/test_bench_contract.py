@@ -26,6 +26,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert j["dtype"] == "f64" and j["data"] == "synthetic" and j["vs_baseline"] is None and j["value"] > 0
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
+    # the workload part of `config` is the CUDA arm's, key for key: the two arms are on the same configuration
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert j["config"] == bench.workload_config("c1", 1_000_000) and j["setup"]["elements_per_step"] == 1_000_000
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -44,7 +49,8 @@ def test_cuda_arm_prints_one_json_line_with_the_contract_keys():
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "4", "--warmup", "3",
-                          "--elems", "80000000", "--e2e-elems", "20000000"], capture_output=True, text=True, env=env, timeout=900)
+                          "--elems", "80000000", "--e2e-elems", "20000000", "--pageable-elems", "10000000", "--sustain-seconds", "0.3"],
+                         capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, out.stdout[-2000:]
@@ -54,8 +60,17 @@ def test_cuda_arm_prints_one_json_line_with_the_contract_keys():
     assert j["value"] > 50 and j["gpu_launches"] >= 4
     r = j["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["algorithmic_bytes_per_launch"] == 24 * 80000000 and r["traffic"] is not None
+    assert r["algorithmic_bytes_per_launch"] == 24 * 80000000 and "traffic" in r and r["traffic_source"]
+    assert r["traffic"] is None or 0.9 * 24 * 80000000 < r["traffic"] < 1.2 * 24 * 80000000
+    sus = r["sustained"]
+    assert sus["seconds"] >= 0.3 and sus["steps"] >= 10 and 0.3 < sus["frac"] < 1.2 and "sm_mhz" in sus["clocks"]
     e = j["e2e"]
     assert e["value"] > 0.5 and e["h2d_bytes_per_step"] == 8 * 20000000 and e["d2h_bytes_per_step"] == 16 * 20000000
+    er = e["roofline"]   # the host link's own ceiling, measured in the run by a bare-copy probe on the same buffers
+    assert er["bound"] in ("pcie", "host_dram") and er["peak_gbs"] > 20 and 0.3 < er["frac"] < 1.15
+    assert abs(er["frac"] - e["value"] / er["peak"]) < 1e-9
+    pg = j["e2e_pageable"]
+    assert pg["value"] > 0.2 and pg["elements_per_gpu"] == 10000000 and "void fabe13_sincos" in pg["path"]
+    assert j["config"]["elements_total"] == 80000000 and j["setup"]["elements_per_gpu"] == 80000000
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] > 0 and j["cpu_baseline"]["cores"] >= 1
     assert "sm_mhz" in j["clocks"] and "reasons" in j["clocks"] and "workload" in j["config"]

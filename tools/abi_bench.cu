@@ -37,7 +37,10 @@ int main(int argc, char** argv) {
     printf("%s\n", fabe13_get_active_implementation_name());
     long long min_n_saved = 0;
     fabe13_cuda_get_option("min_n", &min_n_saved);
+    long long min_np_saved = 0;
+    fabe13_cuda_get_option("min_n_pageable", &min_np_saved);
     fabe13_cuda_set_option("min_n", 0);  // first table: every host-pointer call on the GPU
+    fabe13_cuda_set_option("min_n_pageable", 0);
     printf("%12s %14s %14s %14s %14s %16s %16s\n", "n", "dev wall us", "dev gpu us", "dev Gelem/s", "back2back us", "host pinned us", "host pageable us");
     for (size_t n = 1; n <= nmax; n *= 10) {
         const int reps = n <= 1000000 ? 200 : (n <= 10000000 ? 50 : 10);
@@ -86,19 +89,21 @@ int main(int argc, char** argv) {
     // (min_n = 0: bounce buffer + zero-copy kernel, or the staged pipeline beyond 32768 elements) -- picks "min_n"
     long long min_n_default = 0;
     fabe13_cuda_get_option("min_n", &min_n_default);
-    printf("\nsmall-n route (pageable arrays through void fabe13_sincos; option min_n default %lld)\n", min_n_default);
+    printf("\nsmall-n route (pageable arrays through void fabe13_sincos; options min_n %lld, min_n_pageable %lld)\n", min_n_default, min_np_saved);
     printf("%12s %16s %16s %16s\n", "n", "host core us", "GPU pageable us", "GPU pinned us");
-    const size_t small_sizes[] = {1, 10, 32, 100, 1000, 2000, 4000, 8000, 12000, 16000, 24000, 32000, 65536, 131072, 262144};
+    const size_t small_sizes[] = {1, 10, 32, 100, 1000, 2000, 4000, 8000, 12000, 16000, 24000, 32000, 65536, 131072, 262144, 524288, 1048576};
     for (size_t n : small_sizes) {
         if (n > nmax) break;
         const int reps = n <= 1000 ? 20000 : 2000;
         double t_host = 0, t_gpu = 0, t_pin = 0;
         fabe13_cuda_set_option("min_n", (long long)1 << 31);
+        fabe13_cuda_set_option("min_n_pageable", (long long)1 << 31);
         fabe13_sincos(p_in.data(), p_s.data(), p_c.data(), (int)n);
         double a = now_us();
         for (int i = 0; i < reps; ++i) fabe13_sincos(p_in.data(), p_s.data(), p_c.data(), (int)n);
         t_host = (now_us() - a) / reps;
         fabe13_cuda_set_option("min_n", 0);
+        fabe13_cuda_set_option("min_n_pageable", 0);
         const int greps = 200;
         fabe13_sincos(p_in.data(), p_s.data(), p_c.data(), (int)n);
         a = now_us();
@@ -109,6 +114,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < greps; ++i) fabe13_sincos(h_in, h_s, h_c, (int)n);
         t_pin = (now_us() - a) / greps;
         fabe13_cuda_set_option("min_n", min_n_default);
+        fabe13_cuda_set_option("min_n_pageable", min_np_saved);
         printf("%12zu %16.3f %16.2f %16.2f\n", n, t_host, t_gpu, t_pin);
         fflush(stdout);
     }

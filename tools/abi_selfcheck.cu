@@ -66,6 +66,7 @@ int main() {
         }
     }
     std::vector<double> ps(n), pc(n);
+    fabe13_cuda_set_option("min_n_pageable", 0);
     fabe13_cuda_set_option("min_n", 0);  // the GPU routes of the host entry, also for the 1000-element call below
     fabe13_sincos_host(x.data(), ps.data(), pc.data(), n);
     for (size_t i = 0; i < n; ++i) bad += memcmp(&ps[i], &hs[i], 8) != 0 || memcmp(&pc[i], &hc[i], 8) != 0;

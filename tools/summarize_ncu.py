@@ -5,9 +5,22 @@
 """
 import argparse
 import csv
+import hashlib
 import io
 import json
+import os
 import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KERNEL_SOURCES = ("fabe13_kernels.cu", "fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h")  # = bench.py's list
+
+
+def kernel_source_hash():
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "fabe_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 KEYS = [
     "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
@@ -52,8 +65,11 @@ def main():
         tot = [float(r[i_r]) * scale[units[i_r]] + float(r[i_w]) * scale[units[i_w]] for r in data]
         per = sum(tot) / len(tot) / args.elems
         with open(args.json, "w") as f:
+            # stamped with the kernel sources the capture was taken on (run this right after the GPU call, before
+            # touching them): bench.py carries the figure into roofline.traffic only while the stamp matches
             json.dump({"dram_bytes_per_elem": per, "elements_per_launch": args.elems, "launches": len(tot),
-                       "source": args.report, "metric": "dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full)"}, f, indent=1)
+                       "report": os.path.basename(args.report), "kernel_source_sha256": kernel_source_hash(),
+                       "metric": "dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full)"}, f, indent=1)
         print(f"dram bytes per element: {per:.3f} (algorithmic 24)")
 
 
