@@ -520,7 +520,7 @@ def run_cuda_arm(args):
     sustained = None
     if args.sustain_seconds > 0:
         per_step = max(total_ms / args.steps * 1e-3, 1e-5)
-        k = max(10, int(args.sustain_seconds / per_step) + 1)
+        k = max(10, int(1.1 * args.sustain_seconds / per_step) + 1)  # (steps speed up once the caches and clocks settle)
         barrier()
         sus_sampler = ClockSampler(local).start() if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -55,6 +55,10 @@ __constant__ uint32_t c_ph_stream[FABE13_PH_STREAM_WORDS] = FABE13_PH_STREAM;
 // 2-4 us launch gaps between dependent kernels disappear.  A kernel launched that way must not touch what its
 // predecessor produces before this wait (all prerequisite grids complete, their writes visible).
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ... and the other half: the kernel queued behind this one may be staged (its blocks made resident, parked at their own
+// griddepcontrol.wait) as soon as every block of this grid has started, i.e. during this grid's last wave, instead
+// of after its last block has exited.  It still sees none of this grid's writes before its wait returns.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __global__ void __launch_bounds__(1024) zero_counters_kernel(unsigned int* counters) {
     counters[threadIdx.x] = 0;  // kSegments * kCounterStrideWords == 1024 words
@@ -88,6 +92,7 @@ struct StreamArgs {
     uint32_t local_min;        // warps with at least this many Payne-Hanek lanes reduce them locally (kLocalMin;
                                // 0xFFFFFFFF = never: everything goes to the global worklist, option worklist=1)
     uint32_t dense_hint;       // first-element votes (of 32) that send a warp down the dense route (kDenseHint; 33 = never)
+    uint32_t direct_max;       // a warp with at most this many Payne-Hanek lanes lets each lane reduce its own (kDirectMax)
     Worklist wl;
 };
 
@@ -181,6 +186,10 @@ __device__ __forceinline__ void patch_lane(uint64_t xb, uint64_t& sb, uint64_t& 
 // Measured (tools/tune_thresholds.py, profiles/r01_tune_thresholds.md): with the ~150-instruction round of the current
 // reduction only a LONE lane is cheaper on the global list -> kLocalMin = 2 (option local_min).
 constexpr uint32_t kLocalMin = 2;
+// A warp with only a few Payne-Hanek lanes (at most kDirectMax of its 128 elements) skips the list altogether: the
+// lanes that hold one reduce it themselves, reading the 2/pi words from the constant bank (with one or two lanes
+// active a divergent constant read costs nothing) -- no prefix sum, no compaction, no table staged in shared memory.
+constexpr uint32_t kDirectMax = 4;
 // lanes (of 32) whose first element must be non-plain for the warp to take the dense route
 constexpr uint32_t kDenseHint = 16;
 
@@ -376,16 +385,40 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
 #pragma unroll
             for (int j = 0; j < VEC; ++j) n_huge += is_stashed(xb[u][j]) ? 1u : 0u;
         }
-        if (__ballot_sync(0xFFFFFFFFu, n_huge != 0) != 0) {
+        const uint32_t count_all = __reduce_add_sync(0xFFFFFFFFu, n_huge);
+        const bool to_global = a.wl.counters != nullptr && count_all < a.local_min;  // hybrid launches: stragglers go to the second pass
+        if (count_all != 0 && count_all <= a.direct_max && !to_global) {
+            // a few stragglers: every lane that holds one reduces it itself.  The lane parks its vector in its own
+            // shared-memory slots first (so that the loop below can index it and the registers are free for the
+            // reduction); its result stores follow its own placeholder stores in program order.
+            if (n_huge != 0) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        s_x[warp][(u * VEC + j) * 32 + lane] = xb[u][j];
+                        mask |= (is_stashed(xb[u][j]) ? 1u : 0u) << (u * VEC + j);
+                    }
+                }
+#pragma unroll 1
+                for (; mask != 0; mask &= mask - 1) {
+                    const uint32_t r = (uint32_t)__ffs((int)mask) - 1u;
+                    const size_t e = (size_t)a.head + ((size_t)v0 + (size_t)(r / VEC) * kThreads) * VEC + r % VEC;
+                    store_huge<CORE, OUT>(a, e, s_x[warp][r * 32 + lane], c_ph_stream);
+                }
+            }
+            __syncwarp();  // the slots are reused by the warp's next tile
+        } else if (count_all != 0) {
             uint32_t incl = n_huge;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if ((int)lane >= d) incl += t;
             }
-            const uint32_t count = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t count = count_all;
             uint32_t slot = incl - n_huge;
-            if (count >= a.local_min || a.wl.counters == nullptr) {
+            if (!to_global) {
                 // compact this warp's Payne-Hanek lanes into its shared-memory list ...
                 stage_stream_warp(s_table[warp], lane);
 #pragma unroll
@@ -408,7 +441,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
                 __syncwarp();  // the list is reused by the warp's next tile
             } else {
                 // a few stragglers: leave them, parked in their output slots, to the second-pass kernel
-                grid_dependency_wait();  // the counters must have been zeroed (this kernel may have started early)
+                // (the counters have been zeroed: this grid waited for its predecessors at its top)
                 const uint32_t seg = blockIdx.x % kSegments;
                 uint32_t base = 0;
                 if (lane == 31) base = atomicAdd(a.wl.counters + seg * kCounterStrideWords, count);
@@ -436,6 +469,11 @@ __global__ void __launch_bounds__(kThreads, CORE == FABE13_CORE_PSI ? 4 : FABE13
     sincos_fused_kernel(const StreamArgs a) {
     __shared__ FusedShared<UNROLL, VEC> sh;
     const uint32_t lane = threadIdx.x & 31u;
+    // Every launch of this kernel carries the programmatic-serialisation attribute (option pdl): the kernel queued behind
+    // it -- the second pass of a hybrid call, or the next call's streaming kernel -- is staged during this grid's last
+    // wave; and this grid itself touches nothing before everything queued ahead of it has completed.
+    grid_launch_dependents();
+    grid_dependency_wait();
     if (ONE_TILE) {
         fused_tile<CORE, VEC, UNROLL, WITH_K, OUT>(a, blockIdx.x, sh);
     } else {
@@ -496,7 +534,8 @@ __global__ void __launch_bounds__(kThreads) sincos_second_pass_kernel(const Seco
     __shared__ uint32_t table[FABE13_PH_STREAM_WORDS];
     __shared__ uint32_t seg_start[kSegments + 1];
     __shared__ int overflowed;
-    grid_dependency_wait();  // everything below reads what the stream kernel wrote
+    grid_launch_dependents();  // (the next call's streaming kernel may be staged behind this one)
+    grid_dependency_wait();    // everything below reads what the stream kernel wrote
     if (threadIdx.x < 32) {
         const uint32_t lane = threadIdx.x;
         const uint32_t raw = a.wl.counters[lane * kCounterStrideWords];
@@ -802,12 +841,13 @@ cudaError_t launch_core(const double* d_in, double* d_sin, double* d_cos, long l
     // worklist=1 sends every Payne-Hanek lane to the global list: no local reduction, no dense route
     a.local_min = mode == WL_GLOBAL ? 0xFFFFFFFFu : (uint32_t)(t.local_min > 0 ? t.local_min : (int)kLocalMin);
     a.dense_hint = mode == WL_GLOBAL ? 33u : (uint32_t)(t.dense_hint > 0 ? t.dense_hint : (int)kDenseHint);
+    a.direct_max = mode == WL_GLOBAL ? 0u : (uint32_t)(t.direct_max >= 0 ? t.direct_max : (int)kDirectMax);
 
     if (mode == WL_LOCAL) {  // one launch, no scratch
         a.wl.counters = nullptr;
         a.wl.entries = nullptr;
         a.wl.seg_cap = 0;
-        a.pdl = false;
+        a.pdl = t.pdl != 0;
         *launches += 1;
         return launch_stream<CORE>(a, op, vec, unroll, (int)grid, stream);
     }

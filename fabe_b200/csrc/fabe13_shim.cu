@@ -56,6 +56,7 @@ struct Config {
     std::atomic<long long> hybrid_min_n{(long long)1 << 26};
     std::atomic<long long> local_min{2};
     std::atomic<long long> dense_hint{16};
+    std::atomic<long long> direct_max{4};
     std::atomic<long long> blocks_per_sm{0};
     std::atomic<long long> tiles_per_block{1};
     std::atomic<long long> pdl{1};
@@ -70,9 +71,9 @@ struct Config {
     std::atomic<long long> stream_copy{1};  // staging copies of the pageable path with non-temporal stores
     // host-pointer calls below these many elements stay on the host core: measured crossovers (profiles/r02_abi_latency.txt)
     // of one host thread against the zero-copy kernel (page-locked arrays: 20 us either way at 16k elements) and
-    // against the staged path (pageable arrays: bounce copies + PCIe round trip, 180 vs 290 us at 128k elements)
+    // against the staged path (pageable arrays: bounce copies + PCIe round trip, 360 vs 400 us at 256k elements, equal at 512k)
     std::atomic<long long> min_n{16384};
-    std::atomic<long long> min_n_pageable{131072};
+    std::atomic<long long> min_n_pageable{262144};
     std::atomic<long long> fallback{1};     // void fabe13_sincos(): on a CUDA failure fill the outputs on the host core
     std::atomic<long long> host_threads{0}; // threads of that fallback (0 = auto: the hardware threads, at most 16)
 };
@@ -98,6 +99,7 @@ const OptionDesc kOptions[] = {
     {"hybrid_min_n", "FABE13_CUDA_HYBRID_MIN_N", &Config::hybrid_min_n, 0, (long long)1 << 31},
     {"local_min", "FABE13_CUDA_LOCAL_MIN", &Config::local_min, 1, 129},
     {"dense_hint", "FABE13_CUDA_DENSE_HINT", &Config::dense_hint, 1, 33},
+    {"direct_max", "FABE13_CUDA_DIRECT_MAX", &Config::direct_max, 0, 128},
     {"blocks_per_sm", "FABE13_CUDA_BLOCKS_PER_SM", &Config::blocks_per_sm, 0, 64},
     {"tiles_per_block", "FABE13_CUDA_TILES_PER_BLOCK", &Config::tiles_per_block, 1, 1024},
     {"pdl", "FABE13_CUDA_PDL", &Config::pdl, 0, 1},
@@ -138,6 +140,7 @@ LaunchTuning current_tuning() {
     t.hybrid_min_n = (int)(g_cfg.hybrid_min_n.load() > 0x7FFFFFFFll ? 0x7FFFFFFFll : g_cfg.hybrid_min_n.load());
     t.local_min = (int)g_cfg.local_min.load();
     t.dense_hint = (int)g_cfg.dense_hint.load();
+    t.direct_max = (int)g_cfg.direct_max.load();
     t.blocks_per_sm = (int)g_cfg.blocks_per_sm.load();
     t.tiles_per_block = (int)g_cfg.tiles_per_block.load();
     t.pdl = (int)g_cfg.pdl.load();

@@ -85,7 +85,7 @@ int fabe13_sincos_multi(int ngpu, const int* devices, const double* const* d_in,
 int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_t n);
 
 /* Which host-pointer calls run where.  Below option "min_n" elements (default 16384; FABE13_CUDA_MIN_N) -- below
- * "min_n_pageable" (default 131072) if any of the arrays is pageable memory -- a host-pointer call (fabe13_sincos and
+ * "min_n_pageable" (default 262144) if any of the arrays is pageable memory -- a host-pointer call (fabe13_sincos and
  * every *_host entry) is evaluated on the calling thread by the HOST instantiation of the same per-element core the
  * kernels compile for the device (bit-identical results): a kernel launch plus a synchronisation costs ~13 us, the
  * host core ~1.3 ns per element, and pageable arrays pay two more host copies and a PCIe round trip on top.  Both
@@ -123,7 +123,7 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
  * "worklist" (where arguments >= 2^45 are reduced: 0 = by size [default]: in the streaming kernel's shared memory,
  * one launch, below "hybrid_min_n" elements, plus a global list for sparse stragglers from there on; 1 = global list
  * and second-pass kernel only [the round-1 design]; 2 = shared memory only at every size; 3 = hybrid at every size),
- * "hybrid_min_n", "local_min" / "dense_hint" (routing thresholds of the streaming kernel),
+ * "hybrid_min_n", "local_min" / "dense_hint" / "direct_max" (routing thresholds of the streaming kernel),
  * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
  * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
  * "zero_copy_max", "stream_copy" (staging copies of pageable arrays with non-temporal stores: 1 [default] / 0),

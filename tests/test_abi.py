@@ -212,7 +212,7 @@ def test_small_host_calls_stay_on_the_host_core(fabe13, oracle):
     fabe13/fabe13.c:226-229): they work on a box without one, through every host entry point, count as
     "host_core_calls", launch nothing, and give the bits of the per-element routine the kernels also compile."""
     lib = fabe13._lib.load()
-    assert fabe13.get_option("min_n") == 16384 and fabe13.get_option("min_n_pageable") == 131072
+    assert fabe13.get_option("min_n") == 16384 and fabe13.get_option("min_n_pageable") == 262144
     x = oracle.fill_uniform(8191, 5, -1e6, 1e6)
     x[:8] = [0.0, -0.0, np.inf, np.nan, 1e300, 2.0**45, 5e-324, -1e-9]
     hs, hc, _ = fabe13.host_core(x, 0)

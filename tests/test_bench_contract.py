@@ -63,7 +63,7 @@ def test_cuda_arm_prints_one_json_line_with_the_contract_keys():
     assert r["algorithmic_bytes_per_launch"] == 24 * 80000000 and "traffic" in r and r["traffic_source"]
     assert r["traffic"] is None or 0.9 * 24 * 80000000 < r["traffic"] < 1.2 * 24 * 80000000
     sus = r["sustained"]
-    assert sus["seconds"] >= 0.3 and sus["steps"] >= 10 and 0.3 < sus["frac"] < 1.2 and "sm_mhz" in sus["clocks"]
+    assert sus["seconds"] >= 0.25 and sus["steps"] >= 10 and 0.3 < sus["frac"] < 1.2 and "sm_mhz" in sus["clocks"]
     e = j["e2e"]
     assert e["value"] > 0.5 and e["h2d_bytes_per_step"] == 8 * 20000000 and e["d2h_bytes_per_step"] == 16 * 20000000
     er = e["roofline"]   # the host link's own ceiling, measured in the run by a bare-copy probe on the same buffers

@@ -53,7 +53,7 @@ HEAVY = {"test_c3_1e9_properties", "test_small_n_route_straddles_the_threshold",
 GLOBAL_ONLY = {"test_worklist_capacity_and_overflow", "test_programmatic_dependent_launch_on_and_off",
                "test_host_path_survives_tuning_changes_between_calls"}
 OPTIONS = ("core", "unroll", "blocks_per_sm", "tiles_per_block", "second_pass_blocks_per_sm", "small_n", "worklist_shift",
-           "pdl", "worklist", "hybrid_min_n", "local_min", "dense_hint", "min_n", "min_n_pageable")
+           "pdl", "worklist", "hybrid_min_n", "local_min", "dense_hint", "direct_max", "min_n", "min_n_pageable")
 
 
 @pytest.fixture(autouse=True, params=[0, 1, 3], ids=["auto-worklist", "global-worklist", "hybrid-worklist"])

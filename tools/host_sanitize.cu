@@ -165,7 +165,7 @@ int main() {
         }
     // option table: every documented key, out-of-range values, unknown and empty keys
     const char* keys[] = {"core", "unroll", "blocks_per_sm", "tiles_per_block", "small_n", "worklist", "hybrid_min_n", "local_min",
-                          "dense_hint", "worklist_shift", "second_pass_blocks_per_sm", "pdl", "chunk_elems", "host_devices",
+                          "dense_hint", "direct_max", "worklist_shift", "second_pass_blocks_per_sm", "pdl", "chunk_elems", "host_devices",
                           "stage_threads", "zero_copy_max", "stream_copy", "min_n", "min_n_pageable", "fallback", "host_threads", "launches",
                           "host_core_calls", "fallbacks", "no_such_option", ""};
     for (const char* key : keys) {

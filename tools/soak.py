@@ -48,7 +48,7 @@ def main():
                 "unroll": int(rng.choice([1, 2])), "blocks_per_sm": int(rng.choice([0, 0, 2, 7])), "tiles_per_block": int(rng.choice([1, 3])),
                 "pdl": int(rng.choice([0, 1])), "core": int(rng.choice([0, 0, 1])), "second_pass_blocks_per_sm": int(rng.choice([1, 8, 16])),
                 "worklist": int(rng.choice([0, 0, 1, 2, 3])), "hybrid_min_n": int(rng.choice([1 << 26, 1 << 20])),
-                "local_min": int(rng.choice([2, 2, 1, 4, 129])), "dense_hint": int(rng.choice([16, 16, 1, 24, 33])),
+                "local_min": int(rng.choice([2, 2, 1, 4, 129])), "dense_hint": int(rng.choice([16, 16, 1, 24, 33])), "direct_max": int(rng.choice([4, 4, 0, 1, 16, 128])),
                 "min_n": int(rng.choice([0, 0, 0, 8192])), "min_n_pageable": int(rng.choice([0, 0, 0, 131072]))}  # mostly: every host-pointer call on the GPU, whatever its size
         for k, v in opts.items():
             fb.set_option(k, v)
