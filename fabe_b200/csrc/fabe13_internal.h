@@ -9,13 +9,13 @@
 namespace fabe13 {
 
 struct LaunchTuning {
-    int worklist;       // Payne-Hanek worklist: 0 = by size (local below hybrid_min_n, hybrid from there on);
+    int worklist;       // Payne-Hanek worklist: 0 = by size (local below hybrid_min_n [default: at every size], hybrid from there on);
                         // 1 = global list + second-pass kernel; 2 = warp-local lists in shared memory, one launch,
                         // no scratch; 3 = hybrid (local for warps with >= 4 such lanes, global for stragglers)
     int hybrid_min_n;   // worklist = 0: arrays of at least this many elements take the hybrid sequence
     int local_min;      // hybrid: a warp with at least this many Payne-Hanek lanes (of 128) reduces them itself (default 2)
     int dense_hint;     // first-element votes (of 32) that send a warp down the dense route (default 16; 33 = never)
-    int direct_max;     // a warp with at most this many Payne-Hanek lanes (of 128) lets each lane reduce its own (default 4)
+    int direct_max;     // a warp with at most this many Payne-Hanek lanes (of 128) lets each lane reduce its own (default 2)
     int blocks_per_sm;  // 0 = one tile per block (default); k > 0 = persistent grid of SMs * k blocks
     int tiles_per_block;  // consecutive tiles per block per grid-stride step
     int pdl;              // 1 = queue the launches of one call with programmatic dependent launch

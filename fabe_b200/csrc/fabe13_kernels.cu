@@ -189,7 +189,9 @@ constexpr uint32_t kLocalMin = 2;
 // A warp with only a few Payne-Hanek lanes (at most kDirectMax of its 128 elements) skips the list altogether: the
 // lanes that hold one reduce it themselves, reading the 2/pi words from the constant bank (with one or two lanes
 // active a divergent constant read costs nothing) -- no prefix sum, no compaction, no table staged in shared memory.
-constexpr uint32_t kDirectMax = 4;
+// Measured (tools/tune_stragglers.py, profiles/r02_tune_stragglers.md): 1 % random mix 233 (list only) -> 250 Gelem/s with
+// kDirectMax = 2, 237 with 4 or 8; the global list of the hybrid sequence reaches 213-223 on the same data.
+constexpr uint32_t kDirectMax = 2;
 // lanes (of 32) whose first element must be non-plain for the warp to take the dense route
 constexpr uint32_t kDenseHint = 16;
 
@@ -777,8 +779,8 @@ cudaError_t launch_stream(const StreamArgs& a, int op, int vec, int unroll, int 
 enum { WL_AUTO = 0, WL_GLOBAL = 1, WL_LOCAL = 2, WL_HYBRID = 3 };
 int worklist_mode(size_t n, const LaunchTuning& t) {
     if (t.worklist != WL_AUTO) return t.worklist;
-    // large arrays: the two extra (tiny, PDL-chained) launches of the hybrid sequence cost ~3.5 us per call (1.4 % at
-    // the default threshold, 0.1 % at 1e9) and keep sparse stragglers off the streaming blocks; below that, one launch wins
+    // one launch at every size unless the caller asks for the hybrid sequence from some size on (option hybrid_min_n;
+    // its two extra launches cost 3 % at 1.25e8 elements and it no longer wins on any sparse mix, see kDirectMax)
     return n >= (size_t)t.hybrid_min_n ? WL_HYBRID : WL_LOCAL;
 }
 

@@ -53,10 +53,13 @@ constexpr unsigned long long kPoolKeepBytes = 256ull << 20;  // scratch the stre
 struct Config {
     std::atomic<long long> core{FABE13_CORE_POLY};
     std::atomic<long long> worklist{0};
-    std::atomic<long long> hybrid_min_n{(long long)1 << 26};
+    // worklist = 0: arrays of at least this many elements would take the hybrid sequence (zero counters | stream |
+    // second pass).  Default: never -- with sparse Payne-Hanek lanes reduced by their own lanes (direct_max) the single
+    // launch wins on every mix measured, and costs 3 % less per call at the 8-GPU slice size (profiles/r02_tune_stragglers.md)
+    std::atomic<long long> hybrid_min_n{(long long)1 << 31};
     std::atomic<long long> local_min{2};
     std::atomic<long long> dense_hint{16};
-    std::atomic<long long> direct_max{4};
+    std::atomic<long long> direct_max{2};
     std::atomic<long long> blocks_per_sm{0};
     std::atomic<long long> tiles_per_block{1};
     std::atomic<long long> pdl{1};

@@ -22,9 +22,11 @@ extern "C" {
 
 /* Asynchronous sincos over n device-resident doubles on `cuda_stream` (NULL = legacy default stream).
  * d_in, d_sin, d_cos are device pointers on the current device, 8-byte aligned; d_in == d_sin is allowed.
- * Below 2^26 elements (option "hybrid_min_n") the call is ONE kernel launch and needs no scratch memory: the
- * Payne-Hanek worklists live in shared memory.  From there on, a global worklist for sparse huge arguments
- * (n/32 32-bit entries) is taken from a library-owned stream-ordered memory pool. */
+ * The call is ONE kernel launch (per 2^30 elements) and needs no scratch memory: arguments >= 2^45 are reduced by
+ * Payne-Hanek inside the streaming kernel (by their own lanes when a warp holds one or two, from per-warp lists in
+ * shared memory otherwise).  Option "hybrid_min_n" (default: never) re-enables, from that many elements on, the launch
+ * sequence with a global worklist for sparse huge arguments (n/32 32-bit entries from a library-owned stream-ordered
+ * memory pool) and a second-pass kernel. */
 int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream);
 
 /* Same, and also writes the quadrant index per element (test hook for the k-parity contract):
@@ -120,8 +122,8 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
 
 /* Options: "core" (0/1), "unroll" (1/2), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
  * per SM), "tiles_per_block", "small_n" (below: the one-element-per-thread kernel),
- * "worklist" (where arguments >= 2^45 are reduced: 0 = by size [default]: in the streaming kernel's shared memory,
- * one launch, below "hybrid_min_n" elements, plus a global list for sparse stragglers from there on; 1 = global list
+ * "worklist" (where arguments >= 2^45 are reduced: 0 = by size [default]: inside the streaming kernel, one launch,
+ * below "hybrid_min_n" elements [default 2^31: always], plus a global list for sparse stragglers from there on; 1 = global list
  * and second-pass kernel only [the round-1 design]; 2 = shared memory only at every size; 3 = hybrid at every size),
  * "hybrid_min_n", "local_min" / "dense_hint" / "direct_max" (routing thresholds of the streaming kernel),
  * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",

@@ -97,9 +97,12 @@ def test_options_roundtrip_and_validation(fabe13):
     assert fabe13.get_option("launches") >= 0
     lib = fabe13._lib.load()
     assert fabe13.get_option("worklist") == 0          # default: by size
-    assert lib.fabe13_sincos_workspace_bytes(10**7) == 0                      # warp-local lists in shared memory
-    assert lib.fabe13_sincos_workspace_bytes(10**8) >= 4096 + 4 * (10**8 >> 5)  # hybrid: header + n/32 entries
+    assert lib.fabe13_sincos_workspace_bytes(10**7) == 0                      # reduced inside the streaming kernel
+    assert lib.fabe13_sincos_workspace_bytes(10**9) == 0                      # ... at every size: one launch, no scratch
     try:
+        fabe13.set_option("hybrid_min_n", 1 << 26)     # the hybrid sequence from 2^26 elements on (round-1 default)
+        assert lib.fabe13_sincos_workspace_bytes(10**8) >= 4096 + 4 * (10**8 >> 5)  # header + n/32 entries
+        fabe13.set_option("hybrid_min_n", 1 << 31)
         fabe13.set_option("worklist", 1)               # global worklist alone: header + n/8 32-bit entries
         assert lib.fabe13_sincos_workspace_bytes(10**7) >= 4096 + 4 * (10**7 >> 3)
         fabe13.set_option("worklist", 2)               # local only: never any scratch

@@ -210,8 +210,13 @@ def test_c4_dense_loguniform(fabe13, cuda, oracle, core, small_n):
     assert np.array_equal(bits(s), bits(hs)) and np.array_equal(bits(c), bits(hc)) and np.array_equal(k, hk)
 
 
-def test_c4_sparse_mix_uses_the_worklist(fabe13, cuda, oracle):
+@pytest.mark.parametrize("direct_max", [2, 0, 1, 8, 128])
+def test_c4_sparse_mix_uses_the_worklist(fabe13, cuda, oracle, direct_max):
+    """1 % of the lanes hold extreme values: one or two per warp.  direct_max decides who reduces them -- their own lanes
+    (the default, up to two per warp), the warp's shared-memory list (0), or, in the hybrid / global designs of the
+    fixture, the second-pass kernel.  Same bits every way."""
     fabe13.set_option("small_n", 0)
+    fabe13.set_option("direct_max", direct_max)
     n = 8_000_000
     x = oracle.fill_uniform(n, SEED_C2, -1e4, 1e4)
     h = oracle.fill_loguniform(n, SEED_C4)
