@@ -3,7 +3,7 @@
 // Replaces the reference's SIMD array drivers fabe13_sincos_avx512 / _avx2 / _neon (fabe13/fabe13.c:545-614,
 // :469-541, :399-464) and their scalar tail loops (:339-358).  Kernels:
 //
-//   sincos_fused_kernel       the hot path.  Tiles of 256*UNROLL 256-bit vectors in address order (by default one
+//   sincos_fused_kernel       the hot path.  Tiles of 128*UNROLL 256-bit vectors in address order (by default one
 //                             tile per block, so DRAM sees one advancing window); each thread issues LDG.E.NA.256 for
 //                             its vectors, then two STG.E.EF.256 per vector.  Per lane: reference-exact k, Cody-Waite,
 //                             polynomial/Psi core, integer-pipe rotation.  24 B/element of HBM traffic.  Lanes with
@@ -32,14 +32,18 @@
 namespace fabe13 {
 namespace {
 
+// Blocks of 128 threads (a tile = 512 elements): measured against 256 and 64 in one process
+// (profiles/r02_ab_block_threads_*.txt) -- 1-3 % faster than 256 on plain data at every size (287 vs 270-283 Gelem/s
+// at 1e9, 284 vs 277-282 on the 8-GPU slice, 282 vs 274-277 at 1e8) and 2-4 % on sparse mixes, the same on the dense
+// Payne-Hanek mix; 64-thread blocks lose a quarter (the block scheduler cannot launch them fast enough).
 #ifndef FABE13_BLOCK_THREADS
-#define FABE13_BLOCK_THREADS 256
+#define FABE13_BLOCK_THREADS 128
 #endif
 constexpr int kThreads = FABE13_BLOCK_THREADS;
-// resident blocks per SM the fused kernel is compiled for (register cap 65536 / (256 * 6) -> 40); the Psi core is
-// FP64-pipe bound, needs ~60 registers and is compiled for 4
+// resident blocks per SM the fused kernel is compiled for (register cap 65536 / 1536 threads -> 40); the Psi core is
+// FP64-pipe bound, needs ~60 registers and is compiled for 1024 resident threads
 #ifndef FABE13_FUSED_MIN_BLOCKS
-#define FABE13_FUSED_MIN_BLOCKS 6
+#define FABE13_FUSED_MIN_BLOCKS (1536 / FABE13_BLOCK_THREADS)
 #endif
 // Worklist segments: blocks append to segment blockIdx % kSegments, so same-address atomics (which serialise in
 // L2) are spread over kSegments counters placed one 128-byte line apart.
@@ -467,7 +471,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
 // ONE_TILE: block b owns tile b (the default geometry: no loop state to keep in registers); otherwise blocks stride
 // over chunks of tiles_per_block consecutive tiles.
 template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT, bool ONE_TILE>
-__global__ void __launch_bounds__(kThreads, CORE == FABE13_CORE_PSI ? 4 : FABE13_FUSED_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, CORE == FABE13_CORE_PSI ? 1024 / kThreads : FABE13_FUSED_MIN_BLOCKS)
     sincos_fused_kernel(const StreamArgs a) {
     __shared__ FusedShared<UNROLL, VEC> sh;
     const uint32_t lane = threadIdx.x & 31u;
@@ -620,7 +624,7 @@ __global__ void __launch_bounds__(kThreads) sincos_inline_kernel(const double* i
 // correctly rounded float in all but ~1e-4 of the cases.  12 bytes of HBM traffic per element: one 256-bit load of eight floats
 // per thread, two 256-bit stores; tiles in address order, one per block.
 #ifndef FABE13_SINCOSF_MIN_BLOCKS
-#define FABE13_SINCOSF_MIN_BLOCKS 6
+#define FABE13_SINCOSF_MIN_BLOCKS (1536 / FABE13_BLOCK_THREADS)
 #endif
 struct SincosfArgs {
     const float* in;

@@ -647,8 +647,11 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
             const size_t off = i * chunk;
             const size_t m = n - off < chunk ? n - off : chunk;
             const int slot = (int)(i % kPipeSlots);
+            // the completion event goes behind the slot's LAST chunk only (one record per slot and call: a blocking-sync
+            // event raises an interrupt when it completes, which is not something to put behind every copy)
+            const bool last_on_slot = i + kPipeSlots >= nchunks;
             rc = enqueue_chunk(*ds, slot, in + off, sin_out ? sin_out + off : nullptr, cos_out ? cos_out + off : nullptr, m,
-                               t, core, op, ev[slot]);
+                               t, core, op, last_on_slot ? ev[slot] : nullptr);
         }
         // (also after a failure: earlier chunks are still copying into the caller's arrays -- do not hand the arrays
         // back mid-flight)

@@ -85,6 +85,15 @@ def main():
         for name, lib in libs:
             avg, best = run(lib, x, s, c, 100_000_000, 30)
             print(f"rep {rep} {name:24s} c2 1e8 (30)           avg {avg:7.2f} best {best:7.2f} Gelem/s", flush=True)
+    for rep in range(3):  # the 8-GPU slice of C3: the launch sequence's fixed cost and the grid's tail show here
+        for name, lib in libs:
+            avg, best = run(lib, x, s, c, 125_000_000, 40)
+            print(f"rep {rep} {name:24s} c3 slice 1.25e8 (40)  avg {avg:7.2f} best {best:7.2f} Gelem/s", flush=True)
+    for n_small in (1_000_000, 10_000_000):
+        for rep in range(2):
+            for name, lib in libs:
+                avg, best = run(lib, x, s, c, n_small, 50)
+                print(f"rep {rep} {name:24s} n = {n_small:<9d} (50)     avg {avg:7.2f} best {best:7.2f} Gelem/s", flush=True)
 
 
 if __name__ == "__main__":
