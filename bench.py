@@ -471,6 +471,7 @@ def run_cuda_arm(args):
         return t.item()
 
     max_over_ranks = lambda v: reduce(v, dist.ReduceOp.MAX)
+    min_over_ranks = lambda v: reduce(v, dist.ReduceOp.MIN)
     sum_over_ranks = lambda v: reduce(v, dist.ReduceOp.SUM)
 
     if args.core is not None:
@@ -506,6 +507,7 @@ def run_cuda_arm(args):
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop() if sampler else None
+    fastest_rank_ms = min_over_ranks(total_ms)  # the spread between the GPUs of the box: `value` is set by the slowest
     total_ms = max_over_ranks(total_ms)
     value = n_total * args.steps / (total_ms * 1e-3) / 1e9
 
@@ -567,7 +569,8 @@ def run_cuda_arm(args):
                                                                 "(harness barrier on gloo; NCCL not initialised)",
                       "core": ["poly", "psi"][fb.get_option("core")], "unroll": fb.get_option("unroll"),
                       "blocks_per_sm": fb.get_option("blocks_per_sm"), "worklist": fb.get_option("worklist"),
-                      "hybrid_min_n": fb.get_option("hybrid_min_n"), "implementation": fb.implementation_name()},
+                      "hybrid_min_n": fb.get_option("hybrid_min_n"), "implementation": fb.implementation_name(),
+                      "ms_per_step_slowest_rank": total_ms / args.steps, "ms_per_step_fastest_rank": fastest_rank_ms / args.steps},
             "roofline": roofline,
             "e2e": e2e,
             "e2e_pageable": pageable,
