@@ -242,13 +242,6 @@ done:
     // (huge-reg buffers are left to process exit / the next mmap: munmap needs the unaligned base)
 }
 
-static Shared* new_shared() {
-    void* p = mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
-    if (p == MAP_FAILED) return nullptr;
-    memset(p, 0, sizeof(Shared));
-    return new (p) Shared;
-}
-
 struct Row {
     double h2d_gbs, d2h_gbs;
     bool ok;
@@ -271,61 +264,82 @@ static Row collect(const Cfg& cfg, Shared* sh) {
     return r;
 }
 
-static void release(const Cfg& cfg, Shared* sh) {
-    while (sh->arrived.load() < cfg.ngpu) sched_yield();
-    sh->go.store(1);
+// One (GPU count, style) group of configurations.  CUDA contexts are expensive to create (about a second each on an
+// 8-GPU box), so a group creates them once: style "threads" = ONE forked child that runs every configuration with one
+// thread per GPU; style "procs" = one forked child per GPU (bench.py's layout), each walking the same list of
+// configurations, meeting the others at a barrier in shared memory before every one.  The parent never touches CUDA
+// (fork after CUDA initialisation is not supported).
+struct Group {
+    Shared* sh;   // one Shared per configuration
+    Row* rows;
+    int ncfg;
+};
+
+static Group new_group(int ncfg) {
+    Group g;
+    g.ncfg = ncfg;
+    g.sh = (Shared*)mmap(nullptr, sizeof(Shared) * (size_t)ncfg, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    g.rows = (Row*)mmap(nullptr, sizeof(Row) * (size_t)ncfg, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    memset((void*)g.sh, 0, sizeof(Shared) * (size_t)ncfg);
+    memset((void*)g.rows, 0, sizeof(Row) * (size_t)ncfg);
+    return g;
 }
 
-// style "threads": this process, one thread per GPU.  Must only be called in a process that may initialise CUDA.
-static Row run_threads(const Cfg& cfg) {
-    Shared* sh = new_shared();
-    std::vector<std::thread> th;
-    for (int g = 0; g < cfg.ngpu; ++g) th.emplace_back(worker, cfg, g, g, sh);
-    release(cfg, sh);
-    for (std::thread& t : th) t.join();
-    Row r = collect(cfg, sh);
-    munmap(sh, sizeof(Shared));
-    return r;
+static void free_group(Group& g) {
+    munmap(g.sh, sizeof(Shared) * (size_t)g.ncfg);
+    munmap(g.rows, sizeof(Row) * (size_t)g.ncfg);
 }
 
-// style "procs": one forked child per GPU; the parent has not touched CUDA (fork after CUDA initialisation is not
-// supported), which is why main() itself runs every "threads" configuration in a forked child too.
-static Row run_procs(const Cfg& cfg) {
-    Shared* sh = new_shared();
+static void run_group(const std::vector<Cfg>& cfgs, bool procs, Group& g) {
+    const int ngpu = cfgs[0].ngpu;
     std::vector<pid_t> kids;
-    for (int g = 0; g < cfg.ngpu; ++g) {
+    if (!procs) {
         const pid_t pid = fork();
         if (pid == 0) {
-            worker(cfg, g, g, sh);
+            for (size_t c = 0; c < cfgs.size(); ++c) {
+                Shared* sh = &g.sh[c];
+                std::vector<std::thread> th;
+                for (int d = 0; d < ngpu; ++d) th.emplace_back(worker, cfgs[c], d, d, sh);
+                while (sh->arrived.load() < ngpu) sched_yield();
+                sh->go.store(1);
+                for (std::thread& t : th) t.join();
+                g.rows[c] = collect(cfgs[c], sh);
+            }
             _exit(0);
         }
         kids.push_back(pid);
+    } else {
+        for (int d = 0; d < ngpu; ++d) {
+            const pid_t pid = fork();
+            if (pid == 0) {
+                for (size_t c = 0; c < cfgs.size(); ++c) {
+                    Shared* sh = &g.sh[c];
+                    if (d == 0) {  // rank 0 opens the window once everybody has arrived
+                        std::thread opener([sh, ngpu] {
+                            while (sh->arrived.load() < ngpu) sched_yield();
+                            sh->go.store(1);
+                        });
+                        worker(cfgs[c], d, d, sh);
+                        opener.join();
+                    } else {
+                        worker(cfgs[c], d, d, sh);
+                    }
+                }
+                _exit(0);
+            }
+            kids.push_back(pid);
+        }
     }
-    release(cfg, sh);
+    bool ok = true;
     for (pid_t k : kids) {
         int st = 0;
         waitpid(k, &st, 0);
-        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) sh->failed.store(1);
+        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) ok = false;
     }
-    Row r = collect(cfg, sh);
-    munmap(sh, sizeof(Shared));
-    return r;
-}
-
-static Row run_threads_in_child(const Cfg& cfg) {
-    Row* out = (Row*)mmap(nullptr, sizeof(Row), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
-    memset(out, 0, sizeof(Row));
-    const pid_t pid = fork();
-    if (pid == 0) {
-        *out = run_threads(cfg);
-        _exit(0);
-    }
-    int st = 0;
-    waitpid(pid, &st, 0);
-    Row r = *out;
-    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) r.ok = false;
-    munmap(out, sizeof(Row));
-    return r;
+    if (procs)
+        for (size_t c = 0; c < cfgs.size(); ++c) g.rows[c] = collect(cfgs[c], &g.sh[c]);
+    if (!ok)
+        for (size_t c = 0; c < cfgs.size(); ++c) g.rows[c].ok = false;
 }
 
 // host memory: T threads each read 8 bytes and write 16 per element (non-temporal stores), the CPU arm's traffic mix
@@ -446,6 +460,7 @@ int main(int argc, char** argv) {
     for (int ngpu : counts) {
         if (ngpu > visible || ngpu > 16) continue;
         for (int procs = 0; procs < 2; ++procs) {
+            std::vector<Cfg> cfgs;
             for (int alloc = 0; alloc < ALLOC_COUNT; ++alloc) {
                 for (int bind = 0; bind < 2; ++bind) {
                     for (int dir = 0; dir < 3; ++dir) {
@@ -454,23 +469,29 @@ int main(int argc, char** argv) {
                         if (dir != DIR_BOTH && (alloc != ALLOC_PORTABLE || bind)) continue;
                         if (bind && alloc != ALLOC_PORTABLE && alloc != ALLOC_HUGE_REG) continue;
                         if (quick && (alloc == ALLOC_DEFAULT || alloc == ALLOC_WC_IN || (bind && alloc != ALLOC_PORTABLE))) continue;
-                        Cfg cfg{ngpu, alloc, dir, bind != 0, secs, chunk_mb << 20, depth};
-                        const Row r = procs ? run_procs(cfg) : run_threads_in_child(cfg);
-                        if (!r.ok) {
-                            printf("%5d %8s %9s %5s %5s %10s\n", ngpu, procs ? "procs" : "threads", kAllocName[alloc], bind ? "yes" : "no",
-                                   kDirName[dir], "failed");
-                            continue;
-                        }
-                        // elements/s this traffic corresponds to: bounded by the slower of in/8 and out/16
-                        double ge = 0;
-                        if (dir == DIR_BOTH) ge = (r.h2d_gbs / 8 < r.d2h_gbs / 16 ? r.h2d_gbs / 8 : r.d2h_gbs / 16);
-                        printf("%5d %8s %9s%s %5s %5s %10.1f %10.1f %10.1f %12.2f\n", ngpu, procs ? "procs" : "threads", kAllocName[alloc],
-                               r.huge_kind == 2 ? "*" : (r.huge_kind == 1 ? "+" : " "), bind ? "yes" : "no", kDirName[dir], r.h2d_gbs, r.d2h_gbs,
-                               r.h2d_gbs + r.d2h_gbs, ge);
-                        fflush(stdout);
+                        cfgs.push_back(Cfg{ngpu, alloc, dir, bind != 0, secs, chunk_mb << 20, depth});
                     }
                 }
             }
+            Group g = new_group((int)cfgs.size());
+            run_group(cfgs, procs != 0, g);
+            for (size_t c = 0; c < cfgs.size(); ++c) {
+                const Cfg& cfg = cfgs[c];
+                const Row& r = g.rows[c];
+                if (!r.ok) {
+                    printf("%5d %8s %9s %5s %5s %10s\n", ngpu, procs ? "procs" : "threads", kAllocName[cfg.alloc], cfg.bind ? "yes" : "no",
+                           kDirName[cfg.dir], "failed");
+                    continue;
+                }
+                // elements/s this traffic corresponds to: bounded by the slower of in/8 and out/16
+                double ge = 0;
+                if (cfg.dir == DIR_BOTH) ge = (r.h2d_gbs / 8 < r.d2h_gbs / 16 ? r.h2d_gbs / 8 : r.d2h_gbs / 16);
+                printf("%5d %8s %9s%s %5s %5s %10.1f %10.1f %10.1f %12.2f\n", ngpu, procs ? "procs" : "threads", kAllocName[cfg.alloc],
+                       r.huge_kind == 2 ? "*" : (r.huge_kind == 1 ? "+" : " "), cfg.bind ? "yes" : "no", kDirName[cfg.dir], r.h2d_gbs, r.d2h_gbs,
+                       r.h2d_gbs + r.d2h_gbs, ge);
+            }
+            fflush(stdout);
+            free_group(g);
         }
     }
     printf("(huge-reg: * = MAP_HUGETLB pages, + = transparent huge pages requested with madvise)\n");
