@@ -430,11 +430,34 @@ def run_e2e(fb, torch, args, dev, x, s, c, n_local, world, barrier, max_over_ran
     barrier()
     if float(abs(ps[:1000] - first).max()) != 0.0:
         raise SystemExit("bench.py: pageable host-path results differ from the device-path results")
+    # beside it, for the record: the same call kept on the host (option min_n_pageable raised above n) -- the library's
+    # own core on the host threads.  For pageable arrays the staging copies alone cost more CPU time than the
+    # arithmetic, so this is what a caller without page-locked buffers may prefer; it is not the GPU path and not `e2e`.
+    saved_cut = fb.get_option("min_n_pageable")
+    host_core = None
+    try:
+        fb.set_option("min_n_pageable", 1 << 31)
+        fb.sincos_legacy(px, ps, pc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(pg_steps):
+            fb.sincos_legacy(px, ps, pc)
+        t_hc = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        if float(abs(ps[:1000] - first).max()) != 0.0:
+            raise SystemExit("bench.py: host-core results differ from the device-path results")
+        host_core = {"value": n_pg * world * pg_steps / t_hc / 1e9, "unit": UNIT,
+                     "threads_per_rank": fb.get_option("host_threads") or min(16, os.cpu_count() or 1),
+                     "note": "NOT the GPU path: the same call with option min_n_pageable raised, i.e. the library's host "
+                             "instantiation of the core on the host threads (bit-identical results)"}
+    finally:
+        fb.set_option("min_n_pageable", saved_cut)
     pageable = {"value": n_pg * world * pg_steps / t_pg / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * n_pg, "d2h_bytes_per_step": 16 * n_pg,
                 "elements_per_gpu": n_pg, "steps": pg_steps,
                 "path": "void fabe13_sincos(in, sin_out, cos_out, int n) on malloc'd (numpy) arrays: staged through pinned buffers by "
                         "worker threads (host-memory bound), as a relinked caller of the reference gets it",
-                "stage_threads": fb.get_option("stage_threads") or "auto (3/4 of the hardware threads, at most 16)"}
+                "stage_threads": fb.get_option("stage_threads") or "auto (3/4 of the hardware threads, at most 16)",
+                "kept_on_the_host_instead": host_core}
     return e2e, pageable
 
 

@@ -712,22 +712,31 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
 }
 
 // host-pointer calls below "min_n" elements: the host instantiation of the per-element core (one thread, no CUDA call
-// beyond finding out that `in` is not a device pointer).  Reference: the n < 32 scalar route, fabe13/fabe13.c:226-229.
-bool stays_on_host(const void* in, size_t n) {
+// beyond finding out that none of the arrays is device memory -- ~0.03 us per pointer; a device pointer, or a mix of
+// host and device pointers, takes the ordinary route and is served or refused there).  Reference: the n < 32 scalar
+// route, fabe13/fabe13.c:226-229.
+bool stays_on_host(const void* in, const void* out0, const void* out1, size_t n) {
     if (n >= (size_t)g_cfg.min_n.load(std::memory_order_relaxed)) return false;
-    return device_count() == 0 || classify_byte(in, nullptr) != PTR_DEVICE;
+    if (device_count() == 0) return true;
+    return classify_byte(in, nullptr) != PTR_DEVICE && (!out0 || classify_byte(out0, nullptr) != PTR_DEVICE) &&
+           (!out1 || classify_byte(out1, nullptr) != PTR_DEVICE);
 }
 
 int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int op = FABE13_OP_SINCOS) {
     if (n == 0) return 0;
     load_env();
     if (!in || (!sin_out && !cos_out)) return record(cudaErrorInvalidValue, "null array");
-    if (stays_on_host(in, n)) {
+    if (stays_on_host(in, sin_out, cos_out, n)) {
         fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), 1);
         g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
-    if (device_count() == 0) return record(cudaErrorNoDevice, "no CUDA device is visible");
+    if (device_count() == 0) {  // (without a device every array is pageable host memory)
+        if (n >= (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) return record(cudaErrorNoDevice, "no CUDA device is visible");
+        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), host_core_threads());
+        g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     Range range("fabe13_sincos_host");
     const size_t bytes = n * sizeof(double);
     const PtrKind ki = classify(in, bytes);
@@ -742,8 +751,11 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
     }
     const bool pinned = (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED);
     if (!pinned && n < (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) {
-        // pageable arrays pay two extra host copies and a PCIe round trip: one host thread is faster up to here
-        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), 1);
+        // pageable arrays pay two extra host copies and a PCIe round trip: the host core is faster up to here (the
+        // default cut is the crossover of ONE host thread; from 131072 elements on the array is split over up to
+        // "host_threads" threads, 65536 elements each at least -- which is also what a caller gets who raises the cut
+        // to keep pageable arrays of every size on the CPU: see DESIGN.md 3.5 for when that is the better choice)
+        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), host_core_threads());
         g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
@@ -799,12 +811,17 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     if (n == 0) return 0;
     load_env();
     if (!in || !sin_out || !cos_out) return record(cudaErrorInvalidValue, "fabe13_sincosf_host: null array");
-    if (stays_on_host(in, n)) {
+    if (stays_on_host(in, sin_out, cos_out, n)) {
         fabe13::host_sincosf_array(in, sin_out, cos_out, n, (int)g_cfg.core.load(), 1);
         g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
-    if (device_count() == 0) return record(cudaErrorNoDevice, "no CUDA device is visible");
+    if (device_count() == 0) {
+        if (n >= (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) return record(cudaErrorNoDevice, "no CUDA device is visible");
+        fabe13::host_sincosf_array(in, sin_out, cos_out, n, (int)g_cfg.core.load(), host_core_threads());
+        g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     Range range("fabe13_sincosf_host");
     const size_t bytes = n * sizeof(float);
     const PtrKind ki = classify(in, bytes), ks = classify(sin_out, bytes), kc = classify(cos_out, bytes);
@@ -817,7 +834,7 @@ int run_host_f32(const float* in, float* sin_out, float* cos_out, size_t n) {
     }
     const bool pinned = (ki == PTR_PINNED && ks == PTR_PINNED && kc == PTR_PINNED);
     if (!pinned && n < (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) {
-        fabe13::host_sincosf_array(in, sin_out, cos_out, n, (int)g_cfg.core.load(), 1);
+        fabe13::host_sincosf_array(in, sin_out, cos_out, n, (int)g_cfg.core.load(), host_core_threads());
         g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
@@ -1013,9 +1030,12 @@ int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_
 
 const char* fabe13_get_active_implementation_name(void) {
     static char host_name[160];
+    static std::once_flag host_name_once;
     DeviceState* ds;
     if (device_count() == 0) {
-        snprintf(host_name, sizeof host_name, "CUDA sm_100a (no device visible; host core %s)", fabe13::host_isa_name());
+        std::call_once(host_name_once, [] {
+            snprintf(host_name, sizeof host_name, "CUDA sm_100a (no device visible; host core %s)", fabe13::host_isa_name());
+        });
         return host_name;
     }
     if (current_device_state(&ds) != 0) return "CUDA sm_100a (device initialisation failed)";

@@ -96,7 +96,9 @@ int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_
  * On a CUDA failure every int entry point returns the cudaError_t and leaves the outputs unspecified; the void
  * fabe13_sincos(), which has no error channel (fabe13/fabe13.h:51-56), then fills sin_out / cos_out on the host core
  * (option "fallback" = 1, the default; "host_threads" threads) and the error stays readable through
- * fabe13_cuda_last_error().  Read-only counters: "host_core_calls", "fallbacks". */
+ * fabe13_cuda_last_error().  (An in-place call -- in == sin_out -- whose pipeline failed half way has already
+ * overwritten part of its input; the completion is exact only for calls with separate arrays.)
+ * Read-only counters: "host_core_calls", "fallbacks". */
 
 /* Pinned host allocations for the fast host path. */
 void* fabe13_cuda_host_alloc(size_t bytes);

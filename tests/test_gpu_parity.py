@@ -482,6 +482,15 @@ def test_mixed_host_device_pointers_fail_loudly(fabe13, cuda):
     rc = lib.fabe13_sincos_host(x.ctypes.data, d.data_ptr(), d.data_ptr(), 64)
     assert rc != 0 and lib.fabe13_cuda_last_error() != 0
     lib.fabe13_cuda_clear_error()
+    # ... also below the small-n cut, where host arrays would stay on the host core: a device pointer among them must be
+    # noticed before the host touches it
+    fabe13.set_option("min_n", 16384)
+    for args in ((x.ctypes.data, d.data_ptr(), d.data_ptr()), (x.ctypes.data, x.ctypes.data, d.data_ptr()),
+                 (d.data_ptr(), x.ctypes.data, x.ctypes.data)):
+        assert lib.fabe13_sincos_host(*args, 64) != 0
+        lib.fabe13_cuda_clear_error()
+    assert lib.fabe13_sin_host(x.ctypes.data, d.data_ptr(), 64) != 0
+    lib.fabe13_cuda_clear_error()
 
 
 def test_streams_and_concurrency(fabe13, cuda, oracle):

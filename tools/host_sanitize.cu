@@ -106,7 +106,7 @@ int main() {
         if (fabe13_sin_host(x.data(), as.data(), m) != 0 || memcmp(ws.data(), as.data(), m * 8)) return 1;
         if (fabe13_cos_host(x.data(), ac.data(), m) != 0 || memcmp(wc.data(), ac.data(), m * 8)) return 1;
         if (fabe13_cuda_device_count() == 0) {
-            const size_t big = 200000;
+            const size_t big = 400000;  // above the pageable cut (262144): the GPU route, which cannot run here
             std::vector<double> bx(in.begin(), in.begin() + big), bs(big), bc(big), hs(big), hc(big);
             fabe13_debug_host_core(bx.data(), hs.data(), hc.data(), nullptr, big, 0);
             fabe13_cuda_clear_error();
