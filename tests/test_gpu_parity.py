@@ -484,12 +484,16 @@ def test_mixed_host_device_pointers_fail_loudly(fabe13, cuda):
     lib.fabe13_cuda_clear_error()
     # ... also below the small-n cut, where host arrays would stay on the host core: a device pointer among them must be
     # noticed before the host touches it
+    # (every array is asked about from 256 elements on; below that only `in`, to keep a 10-element call at 0.15 us)
     fabe13.set_option("min_n", 16384)
+    x = np.zeros(1000)
+    d = torch.zeros(1000, dtype=torch.float64, device=cuda)
     for args in ((x.ctypes.data, d.data_ptr(), d.data_ptr()), (x.ctypes.data, x.ctypes.data, d.data_ptr()),
                  (d.data_ptr(), x.ctypes.data, x.ctypes.data)):
-        assert lib.fabe13_sincos_host(*args, 64) != 0
+        assert lib.fabe13_sincos_host(*args, 1000) != 0
         lib.fabe13_cuda_clear_error()
-    assert lib.fabe13_sin_host(x.ctypes.data, d.data_ptr(), 64) != 0
+    assert lib.fabe13_sin_host(x.ctypes.data, d.data_ptr(), 1000) != 0
+    assert lib.fabe13_sincos_host(d.data_ptr(), x.ctypes.data, x.ctypes.data, 10) != 0   # a device `in` is noticed at every size
     lib.fabe13_cuda_clear_error()
 
 
