@@ -74,3 +74,30 @@ def test_cuda_arm_prints_one_json_line_with_the_contract_keys():
     assert j["config"]["elements_total"] == 80000000 and j["setup"]["elements_per_gpu"] == 80000000
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] > 0 and j["cpu_baseline"]["cores"] >= 1
     assert "sm_mhz" in j["clocks"] and "reasons" in j["clocks"] and "workload" in j["config"]
+
+
+def test_ncu_traffic_is_carried_over_only_for_the_kernel_sources_it_was_captured_on(tmp_path, monkeypatch):
+    """roofline.traffic comes from the committed ncu capture (profiles/ncu_traffic.json).  bench.py uses it only while the
+    capture's stamp equals the hash of the kernel sources of this build; otherwise it prints null and says why."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    now = bench.kernel_source_hash()
+    assert len(now) == 64
+    fake_root = tmp_path
+    (fake_root / "profiles").mkdir()
+    (fake_root / "fabe_b200" / "csrc").mkdir(parents=True)
+    for name in bench.KERNEL_SOURCES:
+        (fake_root / "fabe_b200" / "csrc" / name).write_bytes(open(os.path.join(ROOT, "fabe_b200", "csrc", name), "rb").read())
+    monkeypatch.setattr(bench, "ROOT", str(fake_root))
+    assert bench.kernel_source_hash() == now
+    per, why = bench.ncu_traffic_per_elem()
+    assert per is None and "no ncu capture" in why
+    stamp = {"dram_bytes_per_elem": 23.7, "report": "x.ncu-rep", "kernel_source_sha256": now}
+    (fake_root / "profiles" / "ncu_traffic.json").write_text(json.dumps(stamp))
+    per, why = bench.ncu_traffic_per_elem()
+    assert per == 23.7 and now[:12] in why
+    with open(fake_root / "fabe_b200" / "csrc" / bench.KERNEL_SOURCES[0], "ab") as f:
+        f.write(b"\n// edited after the capture\n")
+    per, why = bench.ncu_traffic_per_elem()
+    assert per is None and "not carried over" in why
