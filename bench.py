@@ -407,6 +407,40 @@ def run_e2e(fb, torch, args, dev, x, s, c, n_local, world, barrier, max_over_ran
                                "buffers, all ranks inside one window, measured in this run right before the timed calls; " + why}}
     if n_e2e < n_local:
         e2e["cap"] = f"{n_e2e} of the rank's {n_local} elements (--e2e-elems, or pinned memory did not allow more)"
+    # beside it, for the record and NOT the headline: the same call with option host_assist -- host threads run the
+    # library's host core (same bits) on pieces from the array's tail while the copy-engine pipeline works from its
+    # front.  A host-resident array is bound by PCIe and by the host's memory, so this is what the machine as a whole
+    # can do for a caller who wants it; how the array was split is reported with it.
+    helpers = max(0, host_threads() // world - 1)
+    if helpers > 0 and n_e2e >= fb.get_option("host_assist_min_n") and not args.no_host_assist:
+        last = s[n_e2e - 1000:n_e2e].cpu().numpy()
+        try:
+            fb.set_option("host_assist", helpers)
+            g0, h0 = fb.get_option("assist_gpu_elems"), fb.get_option("assist_host_elems")
+            fb.sincos(hx, out_sin=hs, out_cos=hc)  # warm-up
+            hs[:1000] = 0.0
+            hs[n_e2e - 1000:] = 0.0
+            g0, h0 = fb.get_option("assist_gpu_elems"), fb.get_option("assist_host_elems")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                fb.sincos(hx, out_sin=hs, out_cos=hc)
+            torch.cuda.synchronize()
+            t_as = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            g1, h1 = fb.get_option("assist_gpu_elems"), fb.get_option("assist_host_elems")
+        finally:
+            fb.set_option("host_assist", 0)
+        if float(abs(hs[:1000] - first).max()) != 0.0 or float(abs(hs[n_e2e - 1000:] - last).max()) != 0.0:
+            raise SystemExit("bench.py: host-assisted results differ from the device-path results")
+        gpu_elems, host_elems = sum_over_ranks(float(g1 - g0)), sum_over_ranks(float(h1 - h0))
+        e2e["with_host_assist"] = {
+            "value": n_e2e * world * e2e_steps / t_as / 1e9, "unit": UNIT, "host_threads_per_rank": helpers,
+            "gpu_share": gpu_elems / max(gpu_elems + host_elems, 1.0),
+            "gpu_gelems": gpu_elems / t_as / 1e9, "host_gelems": host_elems / t_as / 1e9,
+            "note": "NOT the headline and off by default (option host_assist): the copy-engine pipeline takes chunks from the front "
+                    "of the pinned array, host threads run the library's host instantiation of the core (bit-identical) on pieces "
+                    "from its back, both claiming from one cursor; gpu_share = fraction of the elements the GPU computed"}
     del hx, hs, hc
     for p in bufs:
         p.free()
@@ -627,6 +661,7 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the sustained run after the timed region (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiling runs only)")
+    ap.add_argument("--no-host-assist", action="store_true", help="skip the host-assisted variant of the end-to-end leg")
     args = ap.parse_args()
     claim_stdout()
     if args.warmup < 3 and args.impl == "cuda":

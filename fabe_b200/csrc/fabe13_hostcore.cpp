@@ -17,6 +17,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include "fabe13_core.h"
 #include "fabe13_hostcore.h"
 
@@ -25,6 +29,7 @@ namespace {
 
 const uint32_t h_ph_stream[FABE13_PH_STREAM_WORDS] = FABE13_PH_STREAM;
 
+constexpr size_t kStreamFrom = (size_t)1 << 20;  // elements (8 MB per array)
 constexpr int kBlock = 128;  // elements per block: inputs are copied to a local array first, so in == sin_out is safe
 
 // one block (m8 <= kBlock elements, a multiple of 8) of plain-path arithmetic; returns the number of lanes that are NOT plain (to be patched by the caller)
@@ -79,9 +84,47 @@ void one(uint64_t xb, uint64_t* sb, uint64_t* cb) {
     fabe13_sincos_one<CORE>(xb, h_ph_stream, sb, cb, &k);
 }
 
+// Results of a LARGE array leave the block buffers with non-temporal stores: nobody reads them again soon, and an
+// ordinary store would first fetch every destination line for ownership -- 40 instead of 24 bytes of memory traffic per
+// element, on a loop that is bound by the host's memory bandwidth once a few threads run it.  8-byte MOVNTI up to the
+// first 32-byte boundary and after the last one, 32-byte VMOVNTDQ between them; the write-combining buffers merge
+// them into whole lines.  The caller fences before it reports completion.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void put_stream_avx2(double* dst, const uint64_t* src, size_t m) {
+    size_t i = 0;
+    for (; i < m && ((uintptr_t)(dst + i) & 31u) != 0; ++i) _mm_stream_si64((long long*)(dst + i), (long long)src[i]);
+    for (; i + 4 <= m; i += 4)
+        _mm256_stream_si256((__m256i*)(dst + i), _mm256_loadu_si256((const __m256i*)(src + i)));
+    for (; i < m; ++i) _mm_stream_si64((long long*)(dst + i), (long long)src[i]);
+}
+void put_stream_sse2(double* dst, const uint64_t* src, size_t m) {
+    for (size_t i = 0; i < m; ++i) _mm_stream_si64((long long*)(dst + i), (long long)src[i]);
+}
+#endif
+
+typedef void (*PutFn)(double*, const uint64_t*, size_t);
+
+void put_plain(double* dst, const uint64_t* src, size_t m) { memcpy(dst, src, m * sizeof(double)); }
+
+PutFn pick_put(bool stream) {
+#if defined(__x86_64__)
+    if (stream) return __builtin_cpu_supports("avx2") ? put_stream_avx2 : put_stream_sse2;
+#endif
+    (void)stream;
+    return put_plain;
+}
+
+void stores_complete(bool stream) {
+#if defined(__x86_64__)
+    if (stream) _mm_sfence();
+#endif
+    (void)stream;
+}
+
 template <int CORE>
-void range(const double* in, double* sin_out, double* cos_out, size_t n, int op) {
+void range(const double* in, double* sin_out, double* cos_out, size_t n, int op, bool stream) {
     static const BlockFn block = pick_block<CORE>();
+    const PutFn put = pick_put(stream);
     alignas(64) double x[kBlock];
     alignas(64) uint64_t s[kBlock], c[kBlock];
     for (size_t off = 0; off < n; off += kBlock) {
@@ -98,9 +141,10 @@ void range(const double* in, double* sin_out, double* cos_out, size_t n, int op)
         if (op != FABE13_OP_SINCOS) {
             for (size_t i = 0; i < m; ++i) s[i] = fabe13_derived_rt(op, fabe13_bits(x[i]), s[i], c[i]);
         }
-        if (sin_out) memcpy(sin_out + off, s, m * sizeof(double));
-        if (cos_out) memcpy(cos_out + off, c, m * sizeof(double));
+        if (sin_out) put(sin_out + off, s, m);
+        if (cos_out) put(cos_out + off, c, m);
     }
+    stores_complete(stream);
 }
 
 template <int CORE>
@@ -162,13 +206,16 @@ double host_derived_one(double x, int op, int core) {
     return fabe13_from_bits(fabe13_derived_rt(op, fabe13_bits(x), fabe13_bits(s), fabe13_bits(c)));
 }
 
-void host_sincos_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads) {
+void host_sincos_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
+                       int stream_stores) {
     if (n == 0 || (!sin_out && !cos_out)) return;
+    // non-temporal result stores from kStreamFrom elements on (an array that size does not stay in the caches anyway)
+    const bool stream = stream_stores > 0 || (stream_stores < 0 && n >= kStreamFrom);
     parallel(n, threads, (size_t)1 << 16, [=](size_t b, size_t e) {
         if (core == FABE13_CORE_PSI)
-            range<FABE13_CORE_PSI>(in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, op);
+            range<FABE13_CORE_PSI>(in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, op, stream);
         else
-            range<FABE13_CORE_POLY>(in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, op);
+            range<FABE13_CORE_POLY>(in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, op, stream);
     });
 }
 

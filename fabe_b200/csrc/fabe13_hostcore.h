@@ -12,8 +12,10 @@ void host_sincosf_one(float x, int core, float* s, float* c);
 double host_derived_one(double x, int op, int core);  // op = FABE13_OP_TAN / _COT / _SINC
 
 // arrays: either output may be null; op = 0 (sincos) or a derived function written to sin_out; in == sin_out allowed.
-// `threads` > 1 splits large arrays (>= 65536 elements per thread) into contiguous pieces.
-void host_sincos_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads);
+// `threads` > 1 splits large arrays (>= 65536 elements per thread) into contiguous pieces.  stream_stores: 1 = write the
+// results with non-temporal stores, 0 = ordinary stores, -1 = by size (non-temporal from 2^20 elements on).
+void host_sincos_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
+                       int stream_stores = -1);
 void host_sincosf_array(const float* in, float* sin_out, float* cos_out, size_t n, int core, int threads);
 
 const char* host_isa_name();  // "AVX-512", "AVX2" or "scalar": the clone of the array loop this CPU runs

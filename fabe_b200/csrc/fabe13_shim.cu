@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -79,6 +80,12 @@ struct Config {
     std::atomic<long long> min_n_pageable{262144};
     std::atomic<long long> fallback{1};     // void fabe13_sincos(): on a CUDA failure fill the outputs on the host core
     std::atomic<long long> host_threads{0}; // threads of that fallback (0 = auto: the hardware threads, at most 16)
+    // Large page-locked host arrays: this many host threads take pieces from the array's TAIL with the host core while
+    // the copy-engine pipeline works through it from the front (0 = off, the default: a host-pointer call is then a
+    // GPU call).  A host-resident array is bound by what the host's memory and the PCIe link carry, not by the kernel
+    // (DESIGN.md 3.5); the host core produces the same bits, so where the two ranges meet makes no difference.
+    std::atomic<long long> host_assist{0};
+    std::atomic<long long> host_assist_min_n{(long long)1 << 24};
 };
 
 Config g_cfg;
@@ -86,6 +93,8 @@ std::once_flag g_cfg_once;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<unsigned long long> g_host_core_calls{0};  // array calls served by the host core (small n)
 std::atomic<unsigned long long> g_fallbacks{0};        // fabe13_sincos calls completed on the host core after a CUDA failure
+std::atomic<unsigned long long> g_assist_host_elems{0};  // option host_assist: elements the host threads took (all calls)
+std::atomic<unsigned long long> g_assist_gpu_elems{0};   // ... and elements the GPU pipeline took in those calls
 std::atomic<int> g_ndev{-1};                           // visible CUDA devices, asked once (-1 = not asked yet)
 thread_local int tl_last_error = 0;                    // per thread: clear / call / check needs no lock
 
@@ -119,6 +128,8 @@ const OptionDesc kOptions[] = {
     {"min_n_pageable", "FABE13_CUDA_MIN_N_PAGEABLE", &Config::min_n_pageable, 0, (long long)1 << 31},
     {"fallback", "FABE13_CUDA_FALLBACK", &Config::fallback, 0, 1},
     {"host_threads", "FABE13_CUDA_HOST_THREADS", &Config::host_threads, 0, 256},
+    {"host_assist", "FABE13_CUDA_HOST_ASSIST", &Config::host_assist, 0, 256},
+    {"host_assist_min_n", "FABE13_CUDA_HOST_ASSIST_MIN_N", &Config::host_assist_min_n, (long long)1 << 20, (long long)1 << 40},
 };
 
 void load_env() {
@@ -208,6 +219,9 @@ struct Range {
     Range(const Range&) = delete;
     Range& operator=(const Range&) = delete;
 };
+
+// results of large arrays leave the host core with non-temporal stores (-1: by size) unless option stream_copy is off
+int host_stream_stores() { return g_cfg.stream_copy.load(std::memory_order_relaxed) != 0 ? -1 : 0; }
 
 int host_core_threads() {
     long long t = g_cfg.host_threads.load();
@@ -605,8 +619,121 @@ void run_workers(int workers, Fn work) {
     for (std::thread& x : th) x.join();
 }
 
-// One device, one contiguous slice.  Caller has made `dev` current.
-int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned, int op) {
+
+// Option host_assist: a large page-locked array worked on from both ends.  The calling thread feeds the copy-engine
+// pipeline with chunks from the FRONT of the array, `helpers` host threads run the host core on pieces from the BACK;
+// both sides claim their next piece from one atomic word (front and back cursor, in units of kAssistUnit elements),
+// so the split follows the speeds of the two sides as they are during this call -- no tuning, no history.  The feeder
+// keeps at most kAssistInFlight chunks queued (it polls the oldest chunk's event: no interrupt per chunk, a sleeping
+// poll every 50 us on 1.3 ms chunks) -- claims must be lazy, or the GPU side would have taken the whole array before
+// the first host thread starts.  Results are the same bits whichever side computes an element.
+constexpr size_t kAssistUnit = (size_t)1 << 18;  // elements per host claim (2 MB per array)
+constexpr int kAssistInFlight = 6;               // chunks queued on the GPU side (three stages, two deep)
+
+int host_slice_assisted(DeviceState& s, int dev, const double* in, double* sin_out, double* cos_out, size_t n, int op,
+                        int helpers, const LaunchTuning& t, int core) {
+    Range range("fabe13:assisted_pipeline");
+    size_t chunk = pick_chunk(n);
+    chunk = (chunk + kAssistUnit - 1) / kAssistUnit * kAssistUnit;  // whole units
+    const uint32_t units_per_chunk = (uint32_t)(chunk / kAssistUnit);
+    const uint32_t units = (uint32_t)((n + kAssistUnit - 1) / kAssistUnit);
+    const size_t need_ws = fabe13::workspace_bytes(chunk, t);
+    std::shared_lock<std::shared_mutex> lk(s.pipe_rw, std::defer_lock);
+    if (int rc = acquire_slots(s, lk, chunk, true, false, need_ws, kPipeSlots)) return rc;
+
+    std::atomic<uint64_t> cursors{(uint64_t)units << 32};  // low word: first unit not yet taken from the front; high word: end of the untaken range
+    std::atomic<int> stop{0};
+    std::atomic<unsigned long long> host_elems{0};
+    auto claim_front = [&](uint32_t want, uint32_t* begin) -> uint32_t {
+        uint64_t c = cursors.load(std::memory_order_relaxed);
+        for (;;) {
+            const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+            if (lo >= hi) return 0;
+            const uint32_t take = hi - lo < want ? hi - lo : want;
+            if (cursors.compare_exchange_weak(c, ((uint64_t)hi << 32) | (lo + take), std::memory_order_relaxed)) {
+                *begin = lo;
+                return take;
+            }
+        }
+    };
+    auto claim_back = [&](uint32_t* begin) -> bool {
+        uint64_t c = cursors.load(std::memory_order_relaxed);
+        for (;;) {
+            const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+            if (lo >= hi) return false;
+            if (cursors.compare_exchange_weak(c, ((uint64_t)(hi - 1) << 32) | lo, std::memory_order_relaxed)) {
+                *begin = hi - 1;
+                return true;
+            }
+        }
+    };
+    auto helper = [&] {
+        Range r("fabe13:host_assist");
+        uint32_t u;
+        unsigned long long mine = 0;
+        while (stop.load(std::memory_order_relaxed) == 0 && claim_back(&u)) {
+            const size_t off = (size_t)u * kAssistUnit;
+            const size_t m = n - off < kAssistUnit ? n - off : kAssistUnit;
+            fabe13::host_sincos_array(in + off, sin_out ? sin_out + off : nullptr, cos_out ? cos_out + off : nullptr, m, op, core, 1,
+                                      host_stream_stores() ? 1 : 0);
+            mine += m;
+        }
+        host_elems.fetch_add(mine, std::memory_order_relaxed);
+    };
+    std::vector<std::thread> th;
+    th.reserve((size_t)helpers);
+    for (int i = 0; i < helpers; ++i) th.emplace_back(helper);
+
+    // the feeder: this thread
+    cudaEvent_t ev[kAssistInFlight] = {};
+    int rc = 0;
+    unsigned long long gpu_elems = 0;
+    for (int i = 0; i < kAssistInFlight && rc == 0; ++i) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) rc = record(e, "cudaEventCreateWithFlags(assist)");
+    }
+    auto wait_event = [&](cudaEvent_t e) -> int {
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(e);
+            if (q == cudaSuccess) return 0;
+            if (q != cudaErrorNotReady) return record(q, "cudaEventQuery(assist)");
+            struct timespec ts = {0, 50000};
+            nanosleep(&ts, nullptr);
+        }
+    };
+    size_t queued = 0;  // chunks enqueued so far; chunk i waits on ev[i % kAssistInFlight]
+    while (rc == 0) {
+        if (queued >= (size_t)kAssistInFlight) rc = wait_event(ev[queued % kAssistInFlight]);  // the oldest chunk in flight
+        if (rc != 0) break;
+        uint32_t u0;
+        const uint32_t got = claim_front(units_per_chunk, &u0);
+        if (got == 0) break;
+        const size_t off = (size_t)u0 * kAssistUnit;
+        size_t m = (size_t)got * kAssistUnit;
+        if (off + m > n) m = n - off;
+        rc = enqueue_chunk(s, (int)(queued % kPipeSlots), in + off, sin_out ? sin_out + off : nullptr, cos_out ? cos_out + off : nullptr, m, t,
+                           core, op, ev[queued % kAssistInFlight]);
+        gpu_elems += m;
+        ++queued;
+    }
+    if (rc != 0) stop.store(1);
+    // (also after a failure: chunks already queued are still copying into the caller's arrays)
+    for (int i = 0; i < kPipeSlots; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(s.slots[i].stream);
+        if (e != cudaSuccess && rc == 0) rc = record(e, "wait for the pipeline (assist)");
+    }
+    for (std::thread& x : th) x.join();
+    for (cudaEvent_t e : ev)
+        if (e) (void)cudaEventDestroy(e);
+    if (rc != 0) (void)cudaGetLastError();
+    g_assist_host_elems.fetch_add(host_elems.load());
+    g_assist_gpu_elems.fetch_add(gpu_elems);
+    (void)dev;
+    return rc;
+}
+
+// One device, one contiguous slice.  Caller has made `dev` current.  `helpers` > 0: option host_assist for this slice.
+int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size_t n, bool pinned, int op, int helpers = 0) {
     DeviceState* ds;
     if (int rc = device_state(dev, &ds)) return rc;
     const LaunchTuning t = current_tuning();
@@ -618,6 +745,8 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
         const int rc = host_small(*ds, in, sin_out, cos_out, n, pinned, t, core, op);
         if (rc >= 0) return rc;
     }
+    if (pinned && helpers > 0 && n >= (size_t)g_cfg.host_assist_min_n.load(std::memory_order_relaxed))
+        return host_slice_assisted(*ds, dev, in, sin_out, cos_out, n, op, helpers, t, core);
     size_t chunk = pick_chunk(n);
     int stage_workers = 0;
     if (!pinned) {
@@ -736,7 +865,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
     }
     if (device_count() == 0) {  // (without a device every array is pageable host memory)
         if (n >= (size_t)g_cfg.min_n_pageable.load(std::memory_order_relaxed)) return record(cudaErrorNoDevice, "no CUDA device is visible");
-        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), host_core_threads());
+        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), host_core_threads(), host_stream_stores());
         g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
@@ -758,7 +887,7 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
         // default cut is the crossover of ONE host thread; from 131072 elements on the array is split over up to
         // "host_threads" threads, 65536 elements each at least -- which is also what a caller gets who raises the cut
         // to keep pageable arrays of every size on the CPU: see DESIGN.md 3.5 for when that is the better choice)
-        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), host_core_threads());
+        fabe13::host_sincos_array(in, sin_out, cos_out, n, op, (int)g_cfg.core.load(), host_core_threads(), host_stream_stores());
         g_host_core_calls.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
@@ -767,7 +896,8 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
     const int ndev_avail = device_count();
     int ndev = (int)g_cfg.host_devices.load();
     if (ndev > ndev_avail) ndev = ndev_avail;
-    if (ndev <= 1 || n < ((size_t)1 << 20)) return host_slice(cur, in, sin_out, cos_out, n, pinned, op);
+    const int helpers = (int)g_cfg.host_assist.load(std::memory_order_relaxed);
+    if (ndev <= 1 || n < ((size_t)1 << 20)) return host_slice(cur, in, sin_out, cos_out, n, pinned, op, helpers);
 
     // contiguous slice per GPU, one host thread each; no exchange between slices
     std::vector<std::thread> th;
@@ -782,7 +912,8 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
                 return;
             }
             if (e > b)
-                rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned, op);
+                rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned, op,
+                                            helpers / ndev);
         });
     }
     for (std::thread& x : th) x.join();
@@ -1018,7 +1149,7 @@ void fabe13_sincos(const double* in, double* sin_out, double* cos_out, int n) {
                                 classify_byte(cos_out, nullptr) == PTR_DEVICE))
         return;  // device memory: nothing the host can do
     const int rc2 = guarded("fabe13_sincos (host fallback)", [&] {
-        fabe13::host_sincos_array(in, sin_out, cos_out, (size_t)n, FABE13_OP_SINCOS, cfg_core(), host_core_threads());
+        fabe13::host_sincos_array(in, sin_out, cos_out, (size_t)n, FABE13_OP_SINCOS, cfg_core(), host_core_threads(), host_stream_stores());
         return 0;
     });
     if (rc2 == 0) {
@@ -1237,6 +1368,14 @@ int fabe13_cuda_get_option(const char* key, long long* value) {
         *value = (long long)g_fallbacks.load();
         return 0;
     }
+    if (strcmp(key, "assist_host_elems") == 0) {
+        *value = (long long)g_assist_host_elems.load();
+        return 0;
+    }
+    if (strcmp(key, "assist_gpu_elems") == 0) {
+        *value = (long long)g_assist_gpu_elems.load();
+        return 0;
+    }
     if (strcmp(key, "device_count") == 0) {
         *value = fabe13_cuda_device_count();
         return 0;
@@ -1273,6 +1412,11 @@ void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, 
 // the host array loop (vectorised clones + patching) as the product calls it, for CPU-only tests of that code
 void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads) {
     fabe13::host_sincos_array(in, sin_out, cos_out, n, op, core, threads);
+}
+
+void fabe13_debug_host_array_stores(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
+                                    int stream_stores) {
+    fabe13::host_sincos_array(in, sin_out, cos_out, n, op, core, threads, stream_stores);
 }
 
 int fabe13_debug_fill_uniform_device(double* d_out, size_t n, unsigned long long seed, unsigned long long first_index,

@@ -98,7 +98,14 @@ int fabe13_sincos_host(const double* in, double* sin_out, double* cos_out, size_
  * (option "fallback" = 1, the default; "host_threads" threads) and the error stays readable through
  * fabe13_cuda_last_error().  (An in-place call -- in == sin_out -- whose pipeline failed half way has already
  * overwritten part of its input; the completion is exact only for calls with separate arrays.)
- * Read-only counters: "host_core_calls", "fallbacks". */
+ * Read-only counters: "host_core_calls", "fallbacks".
+ * Option "host_assist" = k (default 0: off; FABE13_CUDA_HOST_ASSIST) lets k host threads work on a LARGE page-locked
+ * array (at least "host_assist_min_n" elements, default 2^24) together with the GPU: the copy-engine pipeline takes
+ * chunks from the front of the array, the host threads run the host core on pieces from its back, and both claim their
+ * next piece from one shared cursor, so the split follows their speeds during the call.  A host-resident array is
+ * bound by PCIe (78 GB/s for this 8 B in : 16 B out mix = 3.25 Gelem/s per GPU) and by the host's memory, not by the
+ * kernel; the host cores add what the host's memory still carries on top of the link.  The bits do not depend on
+ * where the two sides meet.  Read-only counters "assist_gpu_elems" / "assist_host_elems" tell how such calls were split. */
 
 /* Pinned host allocations for the fast host path. */
 void* fabe13_cuda_host_alloc(size_t bytes);
@@ -130,11 +137,12 @@ void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* e
  * "hybrid_min_n", "local_min" / "dense_hint" / "direct_max" (routing thresholds of the streaming kernel),
  * "worklist_shift" (worklist=1: capacity n >> shift), "second_pass_blocks_per_sm",
  * "pdl" (programmatic dependent launch of the kernels of one call), "chunk_elems", "host_devices", "stage_threads",
- * "zero_copy_max", "stream_copy" (staging copies of pageable arrays with non-temporal stores: 1 [default] / 0),
- * "min_n", "min_n_pageable", "fallback", "host_threads" (see above).
+ * "zero_copy_max", "stream_copy" (non-temporal stores for the staging copies of pageable arrays and for the host
+ * core's results on arrays of 2^20 elements or more: 1 [default] / 0),
+ * "min_n", "min_n_pageable", "fallback", "host_threads", "host_assist", "host_assist_min_n" (see above).
  * Environment variables FABE13_CUDA_<OPTION IN CAPS> set the initial values.
- * Read-only keys for get: "launches" (kernels launched so far), "host_core_calls", "fallbacks", "device_count",
- * "sm_count". */
+ * Read-only keys for get: "launches" (kernels launched so far), "host_core_calls", "fallbacks", "assist_gpu_elems",
+ * "assist_host_elems", "device_count", "sm_count". */
 int fabe13_cuda_set_option(const char* key, long long value);
 int fabe13_cuda_get_option(const char* key, long long* value);
 
@@ -154,6 +162,10 @@ void fabe13_debug_host_derived(const double* in, double* out, size_t n, int op, 
 /* The host ARRAY loop exactly as the small-n route and the fallback run it (vectorised plain path + patched lanes;
  * op = 0 for sincos; either output may be NULL), so CPU-only CI can compare it with the per-element routine. */
 void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads);
+/* ... with the way the results are stored spelled out: stream_stores = 1 non-temporal stores (what arrays of 2^20
+ * elements or more get), 0 ordinary stores, -1 by size. */
+void fabe13_debug_host_array_stores(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
+                                    int stream_stores);
 
 /* Bench/test hooks: fill a device array with the deterministic synthetic inputs used by bench.py and the parity
  * tests (counter-based splitmix64; the same generator exists on the host in oracle/fabe13_oracle.c).

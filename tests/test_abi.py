@@ -153,7 +153,8 @@ def test_every_documented_option_exists_and_round_trips(fabe13):
     library knows no option the header does not name."""
     hdr = open(os.path.join(ROOT, "include", "fabe13_cuda.h")).read()
     block = hdr[hdr.index("/* Options:"):hdr.index("int fabe13_cuda_set_option")]
-    named = set(re.findall(r'"([a-z_0-9]+)"', block)) - {"launches", "device_count", "sm_count", "host_core_calls", "fallbacks"}
+    named = set(re.findall(r'"([a-z_0-9]+)"', block)) - {"launches", "device_count", "sm_count", "host_core_calls", "fallbacks", "assist_gpu_elems",
+                                                               "assist_host_elems"}
     assert len(named) >= 17, named
     for key in sorted(named):
         v = fabe13.get_option(key)          # KeyError = documented but unknown
@@ -240,6 +241,43 @@ def test_small_host_calls_stay_on_the_host_core(fabe13, oracle):
     assert fabe13.get_option("host_core_calls") >= calls + 14 + 6
     assert fabe13.get_option("launches") == launches
     assert lib.fabe13_cuda_last_error() == 0
+
+
+def test_host_core_streaming_stores_give_the_same_bits(fabe13, oracle):
+    """Large arrays leave the host core with non-temporal stores (8-byte up to the first 32-byte boundary and after the
+    last one, 32-byte between): same bits as ordinary stores for every alignment of either output, odd sizes, one
+    output only, in place, several threads -- and nothing is written outside the arrays."""
+    lib = fabe13._lib.load()
+    n = 70_003
+    x = oracle.fill_uniform(n, 21, -1e5, 1e5)
+    x[::97] = oracle.fill_loguniform(len(x[::97]), 22)
+    x[:6] = [0.0, -0.0, np.inf, np.nan, 1e-300, 2.0**45]
+    hs, hc, _ = fabe13.host_core(x, 0)
+    guard = np.float64(-777.25)
+    for a_s in range(4):
+        for a_c in (0, 1, 3):
+            for m, threads in ((n, 1), (n - a_s - 5, 3), (131, 1), (7, 1)):
+                bs, bc = np.full(n + 16, guard), np.full(n + 16, guard)
+                s, c = bs[4 + a_s:4 + a_s + m], bc[4 + a_c:4 + a_c + m]
+                lib.fabe13_debug_host_array_stores(x.ctypes.data, s.ctypes.data, c.ctypes.data, m, 0, 0, threads, 1)
+                assert np.array_equal(bits(s), bits(hs[:m])) and np.array_equal(bits(c), bits(hc[:m])), (a_s, a_c, m)
+                assert np.all(bs[:4 + a_s] == guard) and np.all(bs[4 + a_s + m:] == guard)
+                assert np.all(bc[:4 + a_c] == guard) and np.all(bc[4 + a_c + m:] == guard)
+    only = np.full(n, guard)
+    lib.fabe13_debug_host_array_stores(x.ctypes.data, None, only.ctypes.data, n, 0, 0, 2, 1)
+    assert np.array_equal(bits(only), bits(hc))
+    y = x.copy()                                       # in place
+    lib.fabe13_debug_host_array_stores(y.ctypes.data, y.ctypes.data, only.ctypes.data, n, 0, 0, 2, 1)
+    assert np.array_equal(bits(y), bits(hs))
+    t = np.empty(n)
+    lib.fabe13_debug_host_array_stores(x.ctypes.data, t.ctypes.data, None, n, fabe13.OP_TAN, 0, 2, 1)
+    assert np.array_equal(bits(t), bits(fabe13.host_derived(x, fabe13.OP_TAN)))
+    # by size (-1): 2^20 elements and more stream, the result is the same either way
+    big = oracle.fill_uniform((1 << 20) + 5, 23, -1e4, 1e4)
+    s0, c0, s1, c1 = (np.empty(big.size) for _ in range(4))
+    lib.fabe13_debug_host_array_stores(big.ctypes.data, s0.ctypes.data, c0.ctypes.data, big.size, 0, 0, 4, 0)
+    lib.fabe13_debug_host_array_stores(big.ctypes.data, s1.ctypes.data, c1.ctypes.data, big.size, 0, 0, 4, -1)
+    assert np.array_equal(bits(s0), bits(s1)) and np.array_equal(bits(c0), bits(c1))
 
 
 def test_void_entry_falls_back_to_the_host_core_when_cuda_fails(fabe13, oracle):

@@ -69,6 +69,8 @@ def test_cuda_arm_prints_one_json_line_with_the_contract_keys():
     er = e["roofline"]   # the host link's own ceiling, measured in the run by a bare-copy probe on the same buffers
     assert er["bound"] in ("pcie", "host_dram") and er["peak_gbs"] > 20 and 0.3 < er["frac"] < 1.15
     assert abs(er["frac"] - e["value"] / er["peak"]) < 1e-9
+    ha = e["with_host_assist"]   # reported beside e2e, never instead of it: the same call with option host_assist
+    assert ha["value"] > 0.5 and 0.0 < ha["gpu_share"] <= 1.0 and ha["host_threads_per_rank"] >= 1 and "NOT the headline" in ha["note"]
     pg = j["e2e_pageable"]
     assert pg["value"] > 0.2 and pg["elements_per_gpu"] == 10000000 and "void fabe13_sincos" in pg["path"]
     assert j["config"]["elements_total"] == 80000000 and j["setup"]["elements_per_gpu"] == 80000000

@@ -45,7 +45,7 @@ def gpu_sincos(fabe13, cuda, x):
 # rescan, PDL, caller workspace) are skipped where no global worklist exists.
 HEAVY = {"test_c3_1e9_properties", "test_small_n_route_straddles_the_threshold", "test_trim_and_shutdown_give_memory_back",
          "test_reference_programs_relinked_run_on_the_gpu", "test_partly_registered_arrays_are_staged_not_faulted",
-         "test_concurrent_pinned_callers_share_the_pipeline", "test_sincosf_device_against_libm_rounded_once", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay",
+         "test_concurrent_pinned_callers_share_the_pipeline", "test_host_assist_splits_a_pinned_array_between_gpu_and_host_threads", "test_sincosf_device_against_libm_rounded_once", "test_tan_cot_sinc_host", "test_cuda_graph_capture_and_replay",
          "test_sincosf_device_matches_host_bit_for_bit", "test_sincosf_host_entries",
          "test_cot_of_tiny_arguments_is_not_mistaken_for_a_parked_argument", "test_c5_edge_sweep_full_size_cyclic", "test_more_than_one_launch_sequence",
          "test_c2_uniform_1e4_1e8_device_generated", "test_graft_entry_smoke", "test_torch_ops_registration",
@@ -1180,6 +1180,48 @@ def test_concurrent_pinned_callers_share_the_pipeline(fabe13, cuda, oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_host_assist_splits_a_pinned_array_between_gpu_and_host_threads(fabe13, cuda, oracle):
+    """Option host_assist: the copy-engine pipeline takes chunks from the front of a large page-locked array, host threads
+    run the host core on pieces from its back, both claim from one cursor.  Every element is computed exactly once, the
+    bits do not depend on who computed it (odd size, in place, single output, Payne-Hanek lanes on both sides), and
+    with the option off nothing of the kind happens."""
+    n = 40_000_003
+    px, ps, pc = fabe13.PinnedArray(n), fabe13.PinnedArray(n), fabe13.PinnedArray(n)
+    px.array[:] = oracle.fill_uniform(n, 130, -1e4, 1e4)
+    px.array[3::997] = oracle.fill_loguniform(len(px.array[3::997]), 131)
+    px.array[n - 5:] = [np.inf, np.nan, -0.0, 1e-300, 2.0**45]
+    hs, hc, _ = fabe13.host_core(px.array, 0)
+    g0, h0 = fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")
+    fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)            # option off (default)
+    assert (fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")) == (g0, h0)
+    assert fabe13.get_option("host_assist") == 0
+    try:
+        fabe13.set_option("host_assist", 3)
+        for rep in range(2):
+            ps.array[:] = 0.0
+            pc.array[:] = 0.0
+            launches = fabe13.get_option("launches")
+            fabe13.sincos(px.array, out_sin=ps.array, out_cos=pc.array)
+            g1, h1 = fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")
+            assert (g1 - g0) + (h1 - h0) == n * (rep + 1), (g1 - g0, h1 - h0)
+            assert fabe13.get_option("launches") > launches and g1 > g0      # the GPU did take part ...
+            assert h1 > h0                                                    # ... and so did the host threads
+            assert np.array_equal(bits(ps.array), bits(hs)) and np.array_equal(bits(pc.array), bits(hc))
+        only = fabe13.cos_array(px.array, out=pc.array)                       # single output
+        assert np.array_equal(bits(only), bits(hc))
+        fabe13.sincos(px.array, out_sin=px.array, out_cos=pc.array)          # in place
+        assert np.array_equal(bits(px.array), bits(hs)) and np.array_equal(bits(pc.array), bits(hc))
+        # below host_assist_min_n the option changes nothing
+        g2, h2 = fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")
+        fabe13.sincos(ps.array[:1_000_000], out_sin=pc.array[:1_000_000], out_cos=px.array[:1_000_000])
+        assert (fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")) == (g2, h2)
+    finally:
+        fabe13.set_option("host_assist", 0)
+    assert fabe13._lib.load().fabe13_cuda_last_error() == 0
+    for p in (px, ps, pc):
+        p.free()
 
 
 def test_reference_programs_relinked_run_on_the_gpu(fabe13, cuda):

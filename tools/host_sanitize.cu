@@ -82,6 +82,14 @@ int main() {
             }
             fabe13_debug_host_array(x.data(), nullptr, ac.data(), m, 0, core, 2);
             if (memcmp(wc.data(), ac.data(), m * 8)) return 1;
+            // the same with non-temporal result stores (what large arrays get), outputs at odd 8-byte phases
+            if (m > 3) {
+                fabe13_debug_host_array_stores(x.data(), as.data() + 1, ac.data() + 3, m - 3, 0, core, 2, 1);
+                if (memcmp(ws.data(), as.data() + 1, (m - 3) * 8) || memcmp(wc.data(), ac.data() + 3, (m - 3) * 8)) {
+                    fprintf(stderr, "host array loop with streaming stores differs (m=%zu core=%d)\n", m, core);
+                    return 1;
+                }
+            }
             for (int op = 3; op <= 5; ++op) {
                 fabe13_debug_host_derived(x.data(), ws.data(), m, op, core);
                 fabe13_debug_host_array(x.data(), as.data(), nullptr, m, op, core, 2);
