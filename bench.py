@@ -43,7 +43,7 @@ WORKLOADS = {
 BYTES_PER_ELEM = 24  # 8 B read + 8 B sin + 8 B cos
 METRIC = "fp64_sincos_throughput"
 UNIT = "Gelem/s"
-KERNEL_SOURCES = ("fabe13_kernels.cu", "fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h")
+KERNEL_SOURCES = ("fabe13_kernels.cu", "fabe13_core.h", "fabe13_constants.h", "fabe13_ph_remainders.h", "fabe13_internal.h")
 
 
 def log(*a):

@@ -65,6 +65,7 @@ def signatures():
         "fabe13_debug_host_sincosf": (None, [_vp, _vp, _vp, c.c_size_t, c.c_int]),
         "fabe13_debug_host_derived": (None, [_vp, _vp, c.c_size_t, c.c_int, c.c_int]),
         "fabe13_debug_host_array": (None, [_vp, _vp, _vp, c.c_size_t, c.c_int, c.c_int, c.c_int]),
+        "fabe13_debug_reduce_huge": (None, [_vp, _vp, _vp, _vp, _vp, _vp, c.c_size_t]),
         "fabe13_debug_host_array_stores": (None, [_vp, _vp, _vp, c.c_size_t, c.c_int, c.c_int, c.c_int, c.c_int]),
         "fabe13_cuda_trim": (c.c_int, []),
         "fabe13_cuda_shutdown": (c.c_int, []),

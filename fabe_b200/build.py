@@ -15,7 +15,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libfabe13.so")
 
 SOURCES = ["fabe13_kernels.cu", "fabe13_shim.cu", "fabe13_hostcore.cpp"]
-HEADERS = ["fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h", "fabe13_hostcore.h"]
+HEADERS = ["fabe13_core.h", "fabe13_constants.h", "fabe13_ph_remainders.h", "fabe13_internal.h", "fabe13_hostcore.h"]
 
 
 def _nvcc():

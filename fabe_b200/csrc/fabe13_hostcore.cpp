@@ -229,6 +229,19 @@ void host_sincosf_array(const float* in, float* sin_out, float* cos_out, size_t 
     });
 }
 
+void host_reduce_huge(const double* in, double* r, int* q, double* r_exact, int* q_exact, int* fast_ok, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t xb = fabe13_bits(in[i]);
+        uint32_t qq;
+        r[i] = fabe13_payne_hanek(xb, h_ph_stream, &qq);
+        q[i] = (int)qq;
+        r_exact[i] = fabe13_payne_hanek_exact(xb, h_ph_stream, &qq);
+        q_exact[i] = (int)qq;
+        uint64_t rb;
+        fast_ok[i] = fabe13_payne_hanek_fast(xb, &rb, &qq) ? 1 : 0;
+    }
+}
+
 const char* host_isa_name() {
 #if defined(__x86_64__)
     if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vl"))

@@ -18,6 +18,10 @@ void host_sincos_array(const double* in, double* sin_out, double* cos_out, size_
                        int stream_stores = -1);
 void host_sincosf_array(const float* in, float* sin_out, float* cos_out, size_t n, int core, int threads);
 
+// test hook: the large-argument reduction (2^45 <= |x| < Inf) as the product runs it (r, q), its exact form alone, and
+// whether the fast form vouched for its own result
+void host_reduce_huge(const double* in, double* r, int* q, double* r_exact, int* q_exact, int* fast_ok, size_t n);
+
 const char* host_isa_name();  // "AVX-512", "AVX2" or "scalar": the clone of the array loop this CPU runs
 
 }  // namespace fabe13

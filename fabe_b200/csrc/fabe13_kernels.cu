@@ -199,13 +199,6 @@ constexpr uint32_t kDirectMax = 2;
 // lanes (of 32) whose first element must be non-plain for the warp to take the dense route
 constexpr uint32_t kDenseHint = 16;
 
-// one warp copies the 2/pi word stream into its slice of shared memory (lanes index it by their own exponent; a
-// divergent __constant__ read would serialise)
-__device__ __forceinline__ void stage_stream_warp(uint32_t* dst, uint32_t lane) {
-    dst[lane] = c_ph_stream[lane];
-    if (lane + 32 < FABE13_PH_STREAM_WORDS) dst[lane + 32] = c_ph_stream[lane + 32];
-}
-
 template <int CORE, int OUT>
 __device__ __forceinline__ void store_huge(const StreamArgs& a, size_t e, uint64_t xb, const uint32_t* table) {
     uint64_t sb, cb;
@@ -223,7 +216,6 @@ struct FusedShared {
     // per-warp worklists: no block-wide barrier anywhere, a warp only ever touches its own slice
     uint64_t x[kWarps][kWarpElems];               // arguments of the warp's Payne-Hanek lanes, compacted
     uint64_t c[kWarps][kWarpElems];               // dense route: cosine results on their way back to their lanes
-    uint32_t table[kWarps][FABE13_PH_STREAM_WORDS + 6];  // a private copy of the 2/pi word stream per warp
     uint16_t off[kWarps][kWarpElems];             // their element offsets inside the tile
 };
 
@@ -280,14 +272,12 @@ __device__ __noinline__ void dense_rounds(long long* k_out, uint32_t head, uint3
                                           FusedShared<UNROLL, VEC>& sh) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    stage_stream_warp(sh.table[warp], lane);
-    __syncwarp();  // the table is complete
 #pragma unroll 1
     for (uint32_t r = 0; r < (uint32_t)(UNROLL * VEC); ++r) {
         uint64_t s1, c1;
         int64_t k;
         const uint64_t xr = sh.x[warp][r * 32 + lane];
-        sincos_one_lockstep<CORE>(xr, sh.table[warp], &s1, &c1, &k);
+        sincos_one_lockstep<CORE>(xr, c_ph_stream, &s1, &c1, &k);
         if (out_derived(OUT)) s1 = fabe13_derived<OUT>(xr, s1, c1);
         sh.x[warp][r * 32 + lane] = s1;
         if (out_second(OUT)) sh.c[warp][r * 32 + lane] = c1;
@@ -310,7 +300,6 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
     double* co = out_second(OUT) ? a.cos_out + a.head : nullptr;
     auto& s_x = sh.x;
     auto& s_off = sh.off;
-    auto& s_table = sh.table;
     const uint32_t v0 = tile * (kThreads * UNROLL) + threadIdx.x;
     uint64_t xb[UNROLL][VEC];
     bool live[UNROLL];
@@ -426,7 +415,6 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
             uint32_t slot = incl - n_huge;
             if (!to_global) {
                 // compact this warp's Payne-Hanek lanes into its shared-memory list ...
-                stage_stream_warp(s_table[warp], lane);
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
@@ -443,7 +431,7 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
                 __syncwarp();
                 const size_t tile_base = (size_t)a.head + (size_t)tile * kTileElems;
                 for (uint32_t i = lane; i < count; i += 32)
-                    store_huge<CORE, OUT>(a, tile_base + s_off[warp][i], s_x[warp][i], s_table[warp]);
+                    store_huge<CORE, OUT>(a, tile_base + s_off[warp][i], s_x[warp][i], c_ph_stream);
                 __syncwarp();  // the list is reused by the warp's next tile
             } else {
                 // a few stragglers: leave them, parked in their output slots, to the second-pass kernel

@@ -1414,6 +1414,10 @@ void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out,
     fabe13::host_sincos_array(in, sin_out, cos_out, n, op, core, threads);
 }
 
+void fabe13_debug_reduce_huge(const double* in, double* r, int* q, double* r_exact, int* q_exact, int* fast_ok, size_t n) {
+    fabe13::host_reduce_huge(in, r, q, r_exact, q_exact, fast_ok, n);
+}
+
 void fabe13_debug_host_array_stores(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
                                     int stream_stores) {
     fabe13::host_sincos_array(in, sin_out, cos_out, n, op, core, threads, stream_stores);

@@ -167,6 +167,12 @@ void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out,
 void fabe13_debug_host_array_stores(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
                                     int stream_stores);
 
+/* The reduction of large arguments (2^45 <= |x| < Inf; every in[i] must be in that range) on the host: r[i] and
+ * q[i] = rint(x 2/pi) mod 4 as the product computes them (the fast form: tabulated remainders of the powers of two modulo
+ * 2 pi, then Cody-Waite; the exact 192-bit form where the fast one hands over), r_exact / q_exact from the exact form
+ * alone, fast_ok[i] = 1 where the fast form vouched for its own result. */
+void fabe13_debug_reduce_huge(const double* in, double* r, int* q, double* r_exact, int* q_exact, int* fast_ok, size_t n);
+
 /* Bench/test hooks: fill a device array with the deterministic synthetic inputs used by bench.py and the parity
  * tests (counter-based splitmix64; the same generator exists on the host in oracle/fabe13_oracle.c).
  * uniform: x_i = fma(hi-lo, u_i, lo), u_i in [0,1);  loguniform: |x| log-uniform over [1, 2^1024), random sign. */

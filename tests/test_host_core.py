@@ -48,6 +48,97 @@ def test_payne_hanek_quadrants_are_exact(fabe13, oracle):
     assert np.array_equal(k, want)
 
 
+def _reduce_huge(fabe13, x):
+    lib = fabe13._lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.size
+    r, re = np.empty(n), np.empty(n)
+    q, qe, ok = (np.empty(n, dtype=np.int32) for _ in range(3))
+    lib.fabe13_debug_reduce_huge(x.ctypes.data, r.ctypes.data, q.ctypes.data, re.ctypes.data, qe.ctypes.data, ok.ctypes.data, n)
+    return r, q, re, qe, ok
+
+
+def _huge_from(rng, n, mantissa=None):
+    e = rng.integers(1068, 2047, n).astype(np.uint64)
+    m = rng.integers(0, 1 << 52, n).astype(np.uint64) if mantissa is None else mantissa(rng.integers(0, 1 << 52, n).astype(np.uint64))
+    sgn = rng.integers(0, 2, n).astype(np.uint64)
+    return ((sgn << np.uint64(63)) | (e << np.uint64(52)) | m).view(np.float64)
+
+
+def test_fast_large_argument_reduction_agrees_with_the_exact_one(fabe13):
+    """Arguments >= 2^45 are reduced by the fast form (tabulated remainders of the powers of two modulo 2 pi, TwoSum,
+    Cody-Waite: csrc/fabe13_core.h 2c), which hands the rare result it cannot vouch for to the exact 192-bit form.
+    Over every exponent and over mantissas chosen to hurt the split M = Mh + Ml: the quadrant is ALWAYS the exact one,
+    r is within one ulp of the exact form's r (both are within ~half an ulp of the truth), the fast form vouches for all
+    but ~1e-5 of its results, and where it does not the product returns the exact form's bits."""
+    rng = np.random.default_rng(20261020)
+    low27 = np.uint64((1 << 27) - 1)
+    cases = [
+        _huge_from(rng, 600_000),
+        _huge_from(rng, 100_000, lambda m: m & ~low27),                                          # Ml = 0
+        _huge_from(rng, 100_000, lambda m: (m & ~low27) | (m & np.uint64(3))),                   # Ml = 0 .. 3
+        _huge_from(rng, 100_000, lambda m: m & low27),                                            # Mh minimal
+        _huge_from(rng, 100_000, lambda m: m | low27),                                            # Ml maximal
+        np.ldexp(1.0, np.arange(45, 1024)), -np.ldexp(1.0 + 2.0 ** -52, np.arange(45, 1024)),     # every exponent, extreme mantissas
+        np.ldexp(2.0 - 2.0 ** -52, np.arange(45, 1024)),
+    ]
+    x = np.concatenate(cases)
+    r, q, re, qe, ok = _reduce_huge(fabe13, x)
+    assert np.array_equal(q, qe)
+    assert np.abs(r.view(np.int64) - re.view(np.int64)).max() <= 1
+    assert np.array_equal(bits(r[ok == 0]), bits(re[ok == 0]))
+    assert ok.mean() > 0.9999
+    assert np.all(np.abs(r[ok == 1]) >= 2.0 ** -20) and np.all(np.abs(r[ok == 1]) < 0.7853943487001827)
+
+
+def test_fast_large_argument_reduction_hands_over_where_it_must(fabe13):
+    """Inputs found by search (30e6 random huge doubles) whose remainder lies in one of the two zones the fast form does
+    not vouch for -- |r| < 2^-20 (relative accuracy) and |r| > pi/4 - 2^-18 (the rounding of k) -- plus the double
+    closest to a multiple of pi/2: the fast form reports them, and the product's result is the exact form's."""
+    near_zero = ["0x1.04583f610414bp+164", "0x1.ca3b5a182946dp+798", "0x1.55148d5cb8e00p+747", "0x1.f7f4f6fc7b558p+594",
+                 "0x1.b8dce83231005p+70", "0x1.d395978f3c6ccp+329"]
+    near_tie = ["0x1.d7f618bf16351p+345", "0x1.82ebc2139778ap+741", "0x1.2c902b36da02ep+610", "0x1.3ba460994ce1fp+532",
+                "0x1.c9b83f1554344p+415", "0x1.540e9c14dcf46p+511"]
+    x = np.array([float.fromhex(h) for h in near_zero + near_tie] + [6381956970095103.0 * 2.0 ** 797])
+    x = np.concatenate([x, -x])
+    r, q, re, qe, ok = _reduce_huge(fabe13, x)
+    assert not ok.any()
+    assert np.array_equal(bits(r), bits(re)) and np.array_equal(q, qe)
+    assert np.all(np.abs(r[:6]) < 2.0 ** -20) and np.all(np.abs(r[6:12]) > 0.78539434) and abs(r[12]) < 2.0 ** -60
+
+
+def test_fast_large_argument_reduction_against_mpmath(fabe13):
+    """The remainder itself against 1400-bit arithmetic: r = x - rint(x 2/pi) pi/2 to within 0.501 ulp, q exact."""
+    import mpmath as mp
+
+    mp.mp.prec = 1400
+    rng = np.random.default_rng(7)
+    x = np.abs(_huge_from(rng, 1500))
+    r, q, _, _, ok = _reduce_huge(fabe13, x)
+    pio2 = mp.pi / 2
+    worst = 0.0
+    for xi, ri, qi in zip(x, r, q):
+        xm = mp.mpf(float(xi))
+        k = mp.nint(xm / pio2)
+        true = xm - k * pio2
+        assert int(k) % 4 == qi, xi
+        ulp = 2.0 ** (np.frexp(ri)[1] - 53)
+        worst = max(worst, float(abs(mp.mpf(float(ri)) - true) / ulp))
+    assert worst <= 0.501, worst
+    assert ok.sum() >= 1490
+
+
+def test_ph_remainder_table_is_what_the_generator_produces(tmp_path):
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "rem.h"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_ph_remainders.py"), str(out)], check=True, capture_output=True)
+    assert out.read_text() == open(os.path.join(root, "fabe_b200", "csrc", "fabe13_ph_remainders.h")).read()
+
+
 def test_scalar_api_is_the_array_core(fabe13, oracle):
     x = np.concatenate([oracle.fill_uniform(300, 5, -50.0, 50.0), oracle.fill_loguniform(100, 6)])
     s, c, _ = fabe13.host_core(x, 0)

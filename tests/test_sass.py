@@ -88,23 +88,56 @@ def test_fp32_and_derived_kernels_keep_vector_accesses_and_do_not_spill(sass):
         assert count(body, r"MUFU\.RCP64H") >= 4, name
 
 
-def test_payne_hanek_product_has_no_accumulator_moves(sass):
-    """The 53 x 192-bit product of the Payne-Hanek reduction (csrc/fabe13_core.h) is nine independent IMAD.WIDE with a
-    zero addend plus carry chains.  Its first form (a running 64-bit accumulator per chain) needed two register moves per
-    step to build the next addend pair, which showed up as `VIADD Rx, Ry, URz` with a zeroed uniform register and cost
-    7 % on the extreme-range workload (profiles/r01_ab_ph_multiply.txt).  Checked on the dense-rounds routine of the
-    default hot kernel: the code after its CALL target."""
+def _hot_kernel_functions(sass):
+    """The default hot kernel's SASS split at its out-of-line routines: {call target address: lines from there to the next
+    RET} plus the kernel text itself."""
     (name, body), = pick(sass, r"sincos_fused_kernelILi0ELi4ELi1ELb0ELi0ELb1E").items()
     text = [re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line) for line in body]
-    target = next(re.search(r"CALL\.REL\.NOINC (0x[0-9a-f]+)", line).group(1) for line in text if "CALL.REL.NOINC" in line)
-    start = next(i for i, line in enumerate(text) if f"/*{int(target, 16):04x}*/" in line)
-    dense = text[start:]
+    targets = sorted({int(m.group(1), 16) for line in text for m in [re.search(r"CALL\.REL\.NOINC (0x[0-9a-f]+)", line)] if m})
+    funcs = {}
+    for t in targets:
+        start = next(i for i, line in enumerate(text) if f"/*{t:04x}*/" in line)
+        end = next(i for i in range(start, len(text)) if re.search(r"\bRET\.REL", text[i]))
+        funcs[t] = text[start:end + 1]
+    return name, text, funcs
+
+
+def test_dense_rounds_use_the_fast_reduction_and_keep_the_exact_one_out_of_line(sass):
+    """Arguments >= 2^45 are reduced by the fast form (csrc/fabe13_core.h 2c): one 256-bit read-only load of the lane's
+    table entry and FP64 arithmetic, no integer product.  Checked on the dense-rounds routine of the default hot kernel:
+    its rolled loop holds that load, no IMAD.WIDE, the override vote, and two calls (the exact reduction for the rare
+    hand-over, the override values) -- and it is short: 138 instructions with the 192-bit product inline, 196 before
+    that product was rewritten."""
+    name, text, funcs = _hot_kernel_functions(sass)
+    dense = [f for f in funcs.values() if any(re.search(r"\bBRA\.U\b", line) for line in f)]
+    assert len(dense) == 1, name
+    dense = dense[0]
     loop_end = max(i for i, line in enumerate(dense) if re.search(r"\bBRA\.U\b", line))
-    rounds = dense[:loop_end + 1]
-    wide = [line for line in rounds if "IMAD.WIDE.U32" in line]
+    loop_start = next(i for i, line in enumerate(dense) if re.search(r"\bLDS\.64\b", line))
+    rounds = dense[loop_start:loop_end + 1]
+    assert count(rounds, r"LDG\.E\S*\.256\.CONSTANT") == 1, name      # the table entry: one load per element
+    assert count(rounds, r"IMAD\.WIDE") == 0, name                      # no integer product on the hot path
+    assert count(rounds, r"\b(DFMA|DMUL|DADD)\b") >= 40, name           # reduction (20) + core (15) + the other range's k, r
+    assert count(rounds, r"\bVOTE\.ANY\b") == 1, name                  # the overrides sit behind a warp vote ...
+    assert count(rounds, r"CALL\.REL") == 2, name                       # ... and real branches around two calls
+    assert count(rounds, r"\b(STL|LDL)\b") == 0, name
+    assert len(rounds) <= 130, len(rounds)
+    assert count(dense[:loop_start], r"\bSTS\b") == 0, name            # no 2/pi table is staged any more
+
+
+def test_payne_hanek_product_has_no_accumulator_moves(sass):
+    """The 53 x 192-bit product of the EXACT Payne-Hanek reduction (csrc/fabe13_core.h 2b; out of line since the fast form
+    took over the hot path) is nine independent IMAD.WIDE with a zero addend plus carry chains.  Its first form (a running
+    64-bit accumulator per chain) needed two register moves per step to build the next addend pair, which showed up as
+    `VIADD Rx, Ry, URz` with a zeroed uniform register and cost 7 % on the extreme-range workload
+    (profiles/r01_ab_ph_multiply.txt)."""
+    name, text, funcs = _hot_kernel_functions(sass)
+    exact = [f for f in funcs.values() if count(f, r"IMAD\.WIDE\.U32") >= 7]
+    assert len(exact) == 1, name
+    exact = exact[0]
+    wide = [line for line in exact if "IMAD.WIDE.U32" in line]
     assert 7 <= len(wide) <= 9, wide                               # (two of the nine may be emitted as IMAD.HI / IMAD)
     assert all(re.search(r", RZ ;", line) for line in wide), wide   # independent products: no 64-bit addend
-    assert count(rounds, r"VIADD R\d+, R\d+, UR\d+ ;") <= 1, name   # (the one allowed: the round's shared-memory address)
-    assert count(rounds, r"\bVOTE\.ANY\b") == 1, name               # the overrides sit behind a warp vote ...
-    assert count(rounds, r"CALL\.REL") == 1, name                    # ... and a real branch (around a call)
-    assert len(rounds) <= 175, len(rounds)                          # 196 before the rewrite
+    assert count(exact, r"VIADD R\d+, R\d+, UR\d+ ;") == 0, name
+    assert count(exact, r"\b(STL|LDL)\b") == 0, name
+    assert len(exact) <= 110, len(exact)

@@ -12,7 +12,7 @@ import os
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNEL_SOURCES = ("fabe13_kernels.cu", "fabe13_core.h", "fabe13_constants.h", "fabe13_internal.h")  # = bench.py's list
+KERNEL_SOURCES = ("fabe13_kernels.cu", "fabe13_core.h", "fabe13_constants.h", "fabe13_ph_remainders.h", "fabe13_internal.h")  # = bench.py's list
 
 
 def kernel_source_hash():
