@@ -215,7 +215,6 @@ struct FusedShared {
     static constexpr int kWarps = kThreads / 32;
     // per-warp worklists: no block-wide barrier anywhere, a warp only ever touches its own slice
     uint64_t x[kWarps][kWarpElems];               // arguments of the warp's Payne-Hanek lanes, compacted
-    uint64_t c[kWarps][kWarpElems];               // dense route: cosine results on their way back to their lanes
     uint16_t off[kWarps][kWarpElems];             // their element offsets inside the tile
 };
 
@@ -262,30 +261,55 @@ __device__ __forceinline__ void sincos_one_lockstep(uint64_t x_bits, const uint3
     }
 }
 
-// The rounds of the dense-warp route (see fused_tile).  Not inlined: its register allocation must not leak into the
-// streaming path (inlined, ptxas spilled the fast path's live vectors around it).  The caller has parked the lane's
-// arguments in sh.x[warp][r*32 + lane], r = u*VEC + j, and picks the results up from sh.x (sines) and sh.c (cosines)
-// at the same positions.  (The 256-bit stores stay with the caller: inside this function ptxas 12.9 turned
-// st.global.cs.v4.b64 into a 64-bit store of the first element in one of the two kernels it was cloned into.)
-template <int CORE, int VEC, int UNROLL, bool WITH_K, int OUT>
-__device__ __noinline__ void dense_rounds(long long* k_out, uint32_t head, uint32_t nvec, uint32_t v0,
-                                          FusedShared<UNROLL, VEC>& sh) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (uint32_t r = 0; r < (uint32_t)(UNROLL * VEC); ++r) {
+// The dense-warp route (see fused_tile): one 256-bit vector of every lane through the every-range routine, element by
+// element, all 32 lanes in lockstep.  Not inlined: its register allocation must not leak into the streaming path
+// (inlined, ptxas spilled the fast path's live vectors around it).  Arguments and results travel in registers (the
+// structs are passed and returned by value), and the element loop is unrolled: round 2's first version parked the
+// vector in shared memory and ran a rolled loop over it, and once the fast reduction had taken the integer product
+// out of the rounds, those twelve shared-memory wavefronts per element, next to the 32 of the table gather, were what
+// bound the route -- the L1 data pipe was 96 % busy (profiles/r02_ncu_fused_kernel_c4_rolled_rounds.txt).
+// (The 256-bit stores stay with the caller: inside a non-inlined function ptxas 12.9 once turned st.global.cs.v4.b64
+// into a 64-bit store of the first element in one of the two kernels it was cloned into.)
+// elements per call of the dense routine: the whole vector.  (While its fourth element runs, the routine holds twelve
+// result registers, and ptxas parks three words in local memory once per vector to fit the kernel's 40 registers:
+// six 32-bit local accesses per four elements.  Two calls of two elements each were tried and are worse -- the extra
+// argument shuffling makes both the caller and the routine spill.)
+#ifndef FABE13_DENSE_PIECE
+#define FABE13_DENSE_PIECE 4
+#endif
+constexpr int kDensePiece = FABE13_DENSE_PIECE;
+template <int VEC>
+struct DenseIn {
+    uint64_t x[VEC];
+};
+template <int VEC>
+struct DenseOut {
+    uint64_t s[VEC], c[VEC];
+};
+
+template <int CORE, int VEC, bool WITH_K, int OUT>
+__device__ __forceinline__ DenseOut<VEC> dense_vector_body(const DenseIn<VEC>& in, long long* k_dst) {
+    DenseOut<VEC> o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
         uint64_t s1, c1;
         int64_t k;
-        const uint64_t xr = sh.x[warp][r * 32 + lane];
-        sincos_one_lockstep<CORE>(xr, c_ph_stream, &s1, &c1, &k);
-        if (out_derived(OUT)) s1 = fabe13_derived<OUT>(xr, s1, c1);
-        sh.x[warp][r * 32 + lane] = s1;
-        if (out_second(OUT)) sh.c[warp][r * 32 + lane] = c1;
-        if (WITH_K) {
-            const uint32_t v = v0 + (r / VEC) * kThreads;
-            if (v < nvec) k_out[head + (size_t)v * VEC + r % VEC] = k;
-        }
+        sincos_one_lockstep<CORE>(in.x[j], c_ph_stream, &s1, &c1, &k);
+        if (out_derived(OUT)) s1 = fabe13_derived<OUT>(in.x[j], s1, c1);
+        o.s[j] = s1;
+        o.c[j] = c1;
+        if (WITH_K && k_dst) k_dst[j] = k;
     }
+    return o;
+}
+// (two entry points, so that the ordinary one does not carry a pointer it never uses through its 40 registers)
+template <int CORE, int VEC, int OUT>
+__device__ __noinline__ DenseOut<VEC> dense_vector(const DenseIn<VEC> in) {
+    return dense_vector_body<CORE, VEC, false, OUT>(in, nullptr);
+}
+template <int CORE, int VEC, int OUT>
+__device__ __noinline__ DenseOut<VEC> dense_vector_k(const DenseIn<VEC> in, long long* k_dst) {
+    return dense_vector_body<CORE, VEC, true, OUT>(in, k_dst);
 }
 
 // one tile of kThreads*UNROLL vectors: stream it, then deal with its Payne-Hanek lanes
@@ -320,30 +344,34 @@ __device__ __forceinline__ void fused_tile(const StreamArgs& a, uint32_t tile, F
     // Dense-warp route.  One early vote on each lane's first element (its plain/non-plain predicate is needed by
     // the fast path anyway): if most of them are not plain, the tile is presumably full of Payne-Hanek arguments,
     // and running the fast path first only to redo nearly every lane would waste a quarter of the work.  Such a
-    // warp hands all its elements to the every-range routine instead, one element slot of every lane per round.
-    // Arguments and results pass through the lane's own entries of the warp's shared-memory slice, only so that
-    // the rounds can be a rolled loop (registers cannot be indexed by a loop counter) and the results still leave
-    // as the same two 256-bit stores per vector as on the fast path (scattered 8-byte stores of a dense tile are
-    // bound by L2 sector transactions: measured 98 instead of 120 Gelem/s).  Lanes split for the reduction only
-    // (Payne-Hanek vs Cody-Waite) and share core and fix-up; a round in which no lane holds a Payne-Hanek argument
-    // skips that branch altogether, so interleaved data (every 4th element huge, say) costs one such reduction
-    // per tile, not four.  A wrong guess costs nothing but time: the routine is complete for every input.
+    // warp hands all its elements to the every-range routine instead, one element slot of every lane per round
+    // (dense_vector: out of line, vector in and out in registers), and the results leave as the same two 256-bit
+    // stores per vector as on the fast path (scattered 8-byte stores of a dense tile are bound by L2 sector
+    // transactions: measured 98 instead of 120 Gelem/s).  Lanes split for the reduction only (large-argument form vs
+    // Cody-Waite) and share core and fix-up; a round in which no lane holds a large argument skips that branch
+    // altogether, so interleaved data (every 4th element huge, say) costs one such reduction per tile, not four.
+    // A wrong guess costs nothing but time: the routine is complete for every input.
     if (__popc(__ballot_sync(0xFFFFFFFFu, !fabe13_is_plain(fabe13_abs_hi(xb[0][0])))) >= (int)a.dense_hint) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
+            constexpr int kPiece = VEC < kDensePiece ? VEC : kDensePiece;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) s_x[warp][(u * VEC + j) * 32 + lane] = xb[u][j];
-        }
-        dense_rounds<CORE, VEC, UNROLL, WITH_K, OUT>(a.k_out, a.head, a.nvec, v0, sh);
+            for (int h = 0; h < VEC; h += kPiece) {
+                DenseIn<kPiece> in;
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
+                for (int j = 0; j < kPiece; ++j) in.x[j] = xb[u][h + j];
+                DenseOut<kPiece> o;
+                if (WITH_K)
+                    o = dense_vector_k<CORE, kPiece, OUT>(in, live[u] ? a.k_out + a.head + (size_t)(v0 + u * kThreads) * VEC + h : nullptr);
+                else
+                    o = dense_vector<CORE, kPiece, OUT>(in);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                sb[u][j] = s_x[warp][(u * VEC + j) * 32 + lane];
-                cb[u][j] = out_second(OUT) ? sh.c[warp][(u * VEC + j) * 32 + lane] : 0;
+                for (int j = 0; j < kPiece; ++j) {
+                    sb[u][h + j] = o.s[j];
+                    cb[u][h + j] = o.c[j];
+                }
             }
         }
-        __syncwarp();  // the slice is reused by the warp's next tile
         dense = true;
     } else {
 #pragma unroll

@@ -48,6 +48,34 @@ def device_time(x, steps):
     return ms[len(ms) // 2] * 1e-3, ms[0] * 1e-3, s, c
 
 
+def graph_time(x, calls=20, replays=20):
+    """Small arrays are bound by the cost of issuing a launch from the host (Python + ctypes + one cudaLaunchKernelEx:
+    ~10 us here, 4 us from C), not by the kernel: the same calls replayed from a CUDA graph show what the GPU side takes."""
+    s = torch.empty_like(x)
+    c = torch.empty_like(x)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fb.sincos(x, out_sin=s, out_cos=c)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            fb.sincos(x, out_sin=s, out_cos=c)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(replays + 1)]
+    ev[0].record()
+    for i in range(replays):
+        g.replay()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(replays))
+    return ms[len(ms) // 2] * 1e-3 / calls
+
+
 def host_time(x_dev, n):
     px, ps, pc = fb.PinnedArray(n), fb.PinnedArray(n), fb.PinnedArray(n)
     px.array[:] = x_dev[:n].cpu().numpy()
@@ -139,6 +167,7 @@ def main():
             pool = torch.from_numpy(edge_pool()).to(DEV)
             x = pool.repeat(n // pool.numel() + 1)[:n].contiguous()
         med, best, s, c = device_time(x, steps)
+        replay = graph_time(x) if n <= 4_000_000 else None
         verdict, detail = accuracy(x, s, c)
         n_host = min(n, 100_000_000)
         t_host = host_time(x, n_host)
@@ -146,7 +175,10 @@ def main():
         cpu1, isa = cpu_reference(sample, 1)
         cpun, _ = cpu_reference(x[: min(n, 20_000_000 * threads // 4)].cpu().numpy(), threads)
         gbs = 24 * n / med / 1e9
-        print(f"| {name} | {n:.0e} | {n / med / 1e9:.1f} ({n / best / 1e9:.1f}) | {gbs:.0f} | {gbs / PEAK:.3f} | {gbs / 8000:.3f} | "
+        dev_cell = f"{n / med / 1e9:.1f} ({n / best / 1e9:.1f})"
+        if replay:
+            dev_cell += f"; replayed from a CUDA graph {n / replay / 1e9:.1f} = {24 * n / replay / 1e9 / PEAK:.2f} of measured ({replay * 1e6:.1f} us per call)"
+        print(f"| {name} | {n:.0e} | {dev_cell} | {gbs:.0f} | {gbs / PEAK:.3f} | {gbs / 8000:.3f} | "
               f"{n_host / t_host / 1e9:.2f} | {cpu1:.2f} / {cpun:.2f} ({isa}) | {verdict}: {detail} |", flush=True)
         del x, s, c
     print("\nSmall N (C5, launch-bound): see r01_abi_latency.txt.  Multi-GPU: r01_bench_c3_{2,4,8}gpu.json.")
