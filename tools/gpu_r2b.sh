@@ -10,9 +10,10 @@ SHORT="--steps 3 --warmup 3 --no-e2e --no-cpu-baseline --sustain-seconds 0"
 timeout 800 python -m pytest tests -m gpu -x -q > ${P}_pytest.txt 2>&1; echo "pytest rc=$?" | tee ${P}_rc.txt
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${P}_smoke.txt 2>&1; echo "smoke rc=$?" | tee -a ${P}_rc.txt
 if [ -f $OLD ]; then
-  timeout 300 python tools/ab_plain.py --c4 exact_ph=$OLD loop12=fabe_b200/lib/libfabe13.so:blocks_per_sm=12 > ${P}_ab_c4.txt 2>&1; echo "ab_c4 rc=$?" | tee -a ${P}_rc.txt
+  timeout 300 python tools/ab_plain.py --c4 exact_ph=$OLD rolled=fabe_b200/lib/ab/libfabe13_rolled.so noel=fabe_b200/lib/ab/libfabe13_noel.so > ${P}_ab_c4.txt 2>&1; echo "ab_c4 rc=$?" | tee -a ${P}_rc.txt
 fi
 timeout 200 tools/abi_selfcheck > ${P}_selfcheck.txt 2>&1; echo "selfcheck rc=$?" | tee -a ${P}_rc.txt
+timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > ${P}_bench_ref.json 2> ${P}_bench_ref.err; echo "ref rc=$?" | tee -a ${P}_rc.txt
 timeout 500 python bench.py > ${P}_bench_c3.json 2> ${P}_bench_c3.err; echo "bench rc=$?" | tee -a ${P}_rc.txt
 timeout 200 python bench.py --workload c4 --no-cpu-baseline --no-e2e > ${P}_bench_c4.json 2> ${P}_bench_c4.err; echo "bench c4 rc=$?" | tee -a ${P}_rc.txt
 timeout 120 python bench.py $SHORT --elems 200000000 > ${P}_plain.log 2>&1 &&
@@ -29,6 +30,10 @@ if [ -f $OLD ]; then
 fi
 timeout 300 python tools/run_all_configs.py > ${P}_all_configs.md 2> ${P}_all_configs.err; echo "all_configs rc=$?" | tee -a ${P}_rc.txt
 timeout 200 python tools/derived_timing.py > ${P}_derived.md 2> ${P}_derived.err
+timeout 200 tools/abi_bench > ${P}_abi_bench.txt 2>&1; echo "abi_bench rc=$?" | tee -a ${P}_rc.txt
+timeout 200 python bench.py --workload c2 --no-cpu-baseline --no-e2e > ${P}_bench_c2.json 2> ${P}_bench_c2.err
+timeout 200 python bench.py --core 1 --no-cpu-baseline --no-e2e > ${P}_bench_c3_psi.json 2> ${P}_bench_c3_psi.err
+timeout 200 python tools/accuracy_report.py > ${P}_accuracy.txt 2>&1
 cat ${P}_rc.txt; tail -3 ${P}_pytest.txt; tail -2 ${P}_soak.txt; tail -1 ${P}_selfcheck.txt
 grep "c4 dense" ${P}_ab_c4.txt | tail -6
 python - <<PY
