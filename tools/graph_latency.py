@@ -15,9 +15,15 @@ import fabe_b200 as fb  # noqa: E402
 def main():
     dev = torch.device("cuda:0")
     calls = 200
+    # which kernel serves small arrays: the one-element-per-thread kernel below option small_n (default 2^20), the
+    # streaming kernel (256-bit accesses, programmatic dependent launch) from there on -- python tools/graph_latency.py 0
+    # measures the streaming kernel at every size
+    if len(sys.argv) > 1:
+        fb.set_option("small_n", int(sys.argv[1]))
+    print(f"# small_n = {fb.get_option('small_n')}")
     print("| n per call | direct, us per call | graph replay, us per call |")
     print("|---|---|---|")
-    for n in (10, 1000, 100_000, 1_000_000, 4_000_000):
+    for n in (10, 1000, 10_000, 32_768, 100_000, 300_000, 1_000_000, 2_000_000, 4_000_000):
         x = torch.empty(n, dtype=torch.float64, device=dev).uniform_(-1e4, 1e4)
         s = torch.empty_like(x)
         c = torch.empty_like(x)
