@@ -66,7 +66,12 @@ struct Config {
     std::atomic<long long> pdl{1};
     std::atomic<long long> second_pass_blocks_per_sm{8};
     std::atomic<long long> unroll{1};
-    std::atomic<long long> small_n{(long long)1 << 20};
+    // arrays below this many elements take the one-element-per-thread kernel.  Default 0: the streaming kernel serves every
+    // size -- replayed from a CUDA graph it is the faster one at 1000 elements (1.6 vs 1.8 us per call: its launches are
+    // programmatic-dependent, so back-to-back calls overlap their launch latency) as at 1e6 (3.9 vs 7.0 us: 256-bit
+    // accesses, a quarter of the blocks); only around 1e5 elements the other kernel's larger grid wins, by 7 %
+    // (profiles/r02_graph_latency.md)
+    std::atomic<long long> small_n{0};
     std::atomic<long long> worklist_shift{3};
     std::atomic<long long> chunk_elems{(long long)1 << 22};
     std::atomic<long long> host_devices{1};

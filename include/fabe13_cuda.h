@@ -130,7 +130,7 @@ int fabe13_cuda_shutdown(void);
 void fabe13_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
 
 /* Options: "core" (0/1), "unroll" (1/2), "blocks_per_sm" (0 = one tile per block, k = persistent grid of k blocks
- * per SM), "tiles_per_block", "small_n" (below: the one-element-per-thread kernel),
+ * per SM), "tiles_per_block", "small_n" (arrays below this size take the one-element-per-thread kernel; default 0 = never),
  * "worklist" (where arguments >= 2^45 are reduced: 0 = by size [default]: inside the streaming kernel, one launch,
  * below "hybrid_min_n" elements [default 2^31: always], plus a global list for sparse stragglers from there on; 1 = global list
  * and second-pass kernel only [the round-1 design]; 2 = shared memory only at every size; 3 = hybrid at every size),
