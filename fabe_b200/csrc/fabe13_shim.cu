@@ -702,6 +702,7 @@ int host_slice_assisted(DeviceState& s, int dev, const double* in, double* sin_o
             const cudaError_t q = cudaEventQuery(e);
             if (q == cudaSuccess) return 0;
             if (q != cudaErrorNotReady) return record(q, "cudaEventQuery(assist)");
+            (void)cudaGetLastError();  // "not ready" is no error: do not leave it for the next launch's error check to find
             struct timespec ts = {0, 50000};
             nanosleep(&ts, nullptr);
         }

@@ -20,6 +20,11 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:sinc
 timeout 120 python bench.py $SHORT --workload c4 > ${P}_plain_c4.log 2>&1 &&
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:sincos_fused -s 3 -c 1 -f -o ${P}_prof_fused_c4 \
       python bench.py $SHORT --workload c4 > ${P}_ncu_full_c4.log 2>&1
+timeout 120 python tools/graph_latency.py > ${P}_graph_latency.md 2>&1; timeout 120 python tools/graph_latency.py 1048576 >> ${P}_graph_latency.md 2>&1
+timeout 300 python tools/host_assist_sweep.py > ${P}_host_assist_sweep.md 2>&1
+# A/B of kernel-variant builds, if any were shipped under fabe_b200/lib/ab/ (FABE13_BUILD_DEFINES=... python -m fabe_b200.build <out.so>)
+AB=$(ls fabe_b200/lib/ab/*.so 2>/dev/null | sed 's#.*/libfabe13_\(.*\)\.so#\1=&#' | tr '\n' ' ')
+[ -n "$AB" ] && timeout 300 python tools/ab_plain.py --c4 $AB > ${P}_ab_c4.txt 2>&1
 timeout 300 python tools/run_all_configs.py > ${P}_all_configs.md 2> ${P}_all_configs.err; echo "all_configs rc=$?" | tee -a ${P}_rc.txt
 timeout 200 python tools/derived_timing.py > ${P}_derived.md 2> ${P}_derived.err
 timeout 200 tools/abi_bench > ${P}_abi_bench.txt 2>&1
