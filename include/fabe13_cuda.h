@@ -22,9 +22,11 @@ extern "C" {
 
 /* Asynchronous sincos over n device-resident doubles on `cuda_stream` (NULL = legacy default stream).
  * d_in, d_sin, d_cos are device pointers on the current device, 8-byte aligned; d_in == d_sin is allowed.
- * The call is ONE kernel launch (per 2^30 elements) and needs no scratch memory: arguments >= 2^45 are reduced by
- * Payne-Hanek inside the streaming kernel (by their own lanes when a warp holds one or two, from per-warp lists in
- * shared memory otherwise).  Option "hybrid_min_n" (default: never) re-enables, from that many elements on, the launch
+ * The call is ONE kernel launch (per 2^30 elements) and needs no scratch memory: arguments >= 2^45 are reduced
+ * inside the streaming kernel (by their own lanes when a warp holds one or two, from per-warp lists in shared memory
+ * otherwise, whole warps at once where they are dense) with a 31 KB read-only table of the powers of two modulo 2 pi
+ * followed by Cody-Waite, correctly rounded to half an ulp; the rare remainder that comes out within 2^-20 of 0 or within
+ * 2^-18 of pi/4 is recomputed by an exact 192-bit Payne-Hanek product.  Option "hybrid_min_n" (default: never) re-enables, from that many elements on, the launch
  * sequence with a global worklist for sparse huge arguments (n/32 32-bit entries from a library-owned stream-ordered
  * memory pool) and a second-pass kernel. */
 int fabe13_sincos_device(const double* d_in, double* d_sin, double* d_cos, size_t n, void* cuda_stream);
