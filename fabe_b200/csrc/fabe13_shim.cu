@@ -59,7 +59,11 @@ struct Config {
     // launch wins on every mix measured, and costs 3 % less per call at the 8-GPU slice size (profiles/r02_tune_stragglers.md)
     std::atomic<long long> hybrid_min_n{(long long)1 << 31};
     std::atomic<long long> local_min{2};
-    std::atomic<long long> dense_hint{16};
+    // first-element votes (of 32) that send a warp's tile down the dense route.  8 since the fast reduction made that
+    // route cheap (round 1: 16): the every-range routine over all 128 elements now costs less than fast path + list from
+    // about a fifth of huge arguments on (random 30 / 40 / 50 / 60 %: +5 / +11 / +10 / +4 %, nothing lost below;
+    // profiles/r02_tune_dense_hint.md).  (The kernel file's own kDenseHint only stands in for a non-positive option.)
+    std::atomic<long long> dense_hint{8};
     std::atomic<long long> direct_max{2};
     std::atomic<long long> blocks_per_sm{0};
     std::atomic<long long> tiles_per_block{1};
