@@ -639,8 +639,8 @@ void run_workers(int workers, Fn work) {
 constexpr size_t kAssistUnit = (size_t)1 << 18;  // elements per host claim (2 MB per array)
 constexpr int kAssistInFlight = 6;               // chunks queued on the GPU side (three stages, two deep)
 
-int host_slice_assisted(DeviceState& s, int dev, const double* in, double* sin_out, double* cos_out, size_t n, int op,
-                        int helpers, const LaunchTuning& t, int core) {
+int host_slice_assisted(DeviceState& s, const double* in, double* sin_out, double* cos_out, size_t n, int op, int helpers,
+                        const LaunchTuning& t, int core) {
     Range range("fabe13:assisted_pipeline");
     size_t chunk = pick_chunk(n);
     chunk = (chunk + kAssistUnit - 1) / kAssistUnit * kAssistUnit;  // whole units
@@ -738,7 +738,6 @@ int host_slice_assisted(DeviceState& s, int dev, const double* in, double* sin_o
     if (rc != 0) (void)cudaGetLastError();
     g_assist_host_elems.fetch_add(host_elems.load());
     g_assist_gpu_elems.fetch_add(gpu_elems);
-    (void)dev;
     return rc;
 }
 
@@ -756,7 +755,7 @@ int host_slice(int dev, const double* in, double* sin_out, double* cos_out, size
         if (rc >= 0) return rc;
     }
     if (pinned && helpers > 0 && n >= (size_t)g_cfg.host_assist_min_n.load(std::memory_order_relaxed))
-        return host_slice_assisted(*ds, dev, in, sin_out, cos_out, n, op, helpers, t, core);
+        return host_slice_assisted(*ds, in, sin_out, cos_out, n, op, helpers, t, core);
     size_t chunk = pick_chunk(n);
     int stage_workers = 0;
     if (!pinned) {
