@@ -169,13 +169,21 @@ void parallel(size_t n, int threads, size_t min_per_thread, Fn fn) {
     }
     const size_t per = ((n / (size_t)threads) + kBlock - 1) / kBlock * kBlock;
     std::vector<std::thread> th;
-    for (int t = 1; t < threads; ++t) {
-        const size_t b = per * (size_t)t;
-        if (b >= n) break;
-        const size_t e = (t == threads - 1 || b + per > n) ? n : b + per;
-        th.emplace_back([=] { fn(b, e); });
+    th.reserve((size_t)threads);
+    size_t done_to = per < n ? per : n;  // [0, done_to) is the calling thread's piece; pieces behind it go to threads
+    try {
+        for (int t = 1; t < threads; ++t) {
+            const size_t b = per * (size_t)t;
+            if (b >= n) break;
+            const size_t e = (t == threads - 1 || b + per > n) ? n : b + per;
+            th.emplace_back([=] { fn(b, e); });
+            done_to = e;
+        }
+    } catch (...) {  // a thread could not be started: what it and its successors would have done runs here (below)
     }
     fn((size_t)0, per < n ? per : n);
+    const size_t threaded_end = th.empty() ? (per < n ? per : n) : done_to;
+    if (threaded_end < n) fn(threaded_end, n);
     for (std::thread& x : th) x.join();
 }
 

@@ -622,9 +622,17 @@ void run_workers(int workers, Fn work) {
         work(0);
         return;
     }
+    // (a thread that cannot be started must not take the process down -- a joinable std::thread destroyed during
+    // unwinding calls std::terminate -- nor leave its share of the chunks undone: the calling thread runs it)
     std::vector<std::thread> th;
-    for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
+    th.reserve((size_t)workers);
+    int started = 1;
+    try {
+        for (; started < workers; ++started) th.emplace_back(work, started);
+    } catch (...) {
+    }
     work(0);
+    for (int w = started; w < workers; ++w) work(w);
     for (std::thread& x : th) x.join();
 }
 
@@ -691,7 +699,10 @@ int host_slice_assisted(DeviceState& s, const double* in, double* sin_out, doubl
     };
     std::vector<std::thread> th;
     th.reserve((size_t)helpers);
-    for (int i = 0; i < helpers; ++i) th.emplace_back(helper);
+    try {
+        for (int i = 0; i < helpers; ++i) th.emplace_back(helper);
+    } catch (...) {  // fewer helpers than asked for: the array is finished by those that did start and by the pipeline
+    }
 
     // the feeder: this thread
     cudaEvent_t ev[kAssistInFlight] = {};
@@ -910,22 +921,28 @@ int run_host(const double* in, double* sin_out, double* cos_out, size_t n, int o
 
     // contiguous slice per GPU, one host thread each; no exchange between slices
     std::vector<std::thread> th;
+    th.reserve((size_t)ndev);
     std::vector<int> rcs((size_t)ndev, 0);
-    for (int g = 0; g < ndev; ++g) {
-        th.emplace_back([&, g] {
-            size_t b, e;
-            fabe13_shard_bounds(n, ndev, g, &b, &e);
-            const int dev = (cur + g) % ndev_avail;
-            if (cudaSetDevice(dev) != cudaSuccess) {
-                rcs[(size_t)g] = record(cudaErrorInvalidDevice, "cudaSetDevice(slice)");
-                return;
-            }
-            if (e > b)
-                rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned, op,
-                                            helpers / ndev);
-        });
+    auto slice = [&](int g) {
+        size_t b, e;
+        fabe13_shard_bounds(n, ndev, g, &b, &e);
+        const int dev = (cur + g) % ndev_avail;
+        if (cudaSetDevice(dev) != cudaSuccess) {
+            rcs[(size_t)g] = record(cudaErrorInvalidDevice, "cudaSetDevice(slice)");
+            return;
+        }
+        if (e > b)
+            rcs[(size_t)g] = host_slice(dev, in + b, sin_out ? sin_out + b : nullptr, cos_out ? cos_out + b : nullptr, e - b, pinned, op,
+                                        helpers / ndev);
+    };
+    int started = 0;
+    try {
+        for (; started < ndev; ++started) th.emplace_back(slice, started);
+    } catch (...) {
     }
     for (std::thread& x : th) x.join();
+    for (int g = started; g < ndev; ++g) slice(g);  // threads that could not be started: their slices run here, one by one
+    (void)cudaSetDevice(cur);
     for (int rc : rcs)
         if (rc) return adopt(rc);
     return 0;

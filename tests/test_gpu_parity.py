@@ -1217,6 +1217,31 @@ def test_host_assist_splits_a_pinned_array_between_gpu_and_host_threads(fabe13, 
         g2, h2 = fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")
         fabe13.sincos(ps.array[:1_000_000], out_sin=pc.array[:1_000_000], out_cos=px.array[:1_000_000])
         assert (fabe13.get_option("assist_gpu_elems"), fabe13.get_option("assist_host_elems")) == (g2, h2)
+        # two callers at once, each with its own helpers: they share the pipeline's slots and nothing else
+        import threading
+
+        half = 20_000_000
+        px.array[:] = oracle.fill_uniform(n, 132, -1e4, 1e4)
+        want_s, want_c, _ = fabe13.host_core(px.array[:2 * half], 0)
+        errors = []
+
+        def caller(lo):
+            try:
+                for _ in range(2):
+                    ps.array[lo:lo + half] = 0.0
+                    fabe13.sincos(px.array[lo:lo + half], out_sin=ps.array[lo:lo + half], out_cos=pc.array[lo:lo + half])
+                    if not (np.array_equal(bits(ps.array[lo:lo + half]), bits(want_s[lo:lo + half])) and
+                            np.array_equal(bits(pc.array[lo:lo + half]), bits(want_c[lo:lo + half]))):
+                        errors.append(("bits", lo))
+            except Exception as e:  # noqa: BLE001
+                errors.append((lo, repr(e)))
+
+        threads = [threading.Thread(target=caller, args=(lo,)) for lo in (0, half)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
     finally:
         fabe13.set_option("host_assist", 0)
     assert fabe13._lib.load().fabe13_cuda_last_error() == 0
