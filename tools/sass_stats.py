@@ -5,8 +5,9 @@ library without a GPU.
     python tools/sass_stats.py [library.so] 'sincos_fused_kernelILi0ELi4ELi1ELb0ELi0ELb1'   (substring of the mangled name)
 
 Prints the kernel's total instruction count, every loop (a backward branch and its target) with its length and its
-instruction mix, and the call targets.  The dense-warp rounds of the fused kernel are the loop that holds the nine
-IMAD.WIDE.U32 of the Payne-Hanek product."""
+instruction mix, and the call targets.  (Until the middle of round 2 the dense-warp rounds of the fused kernel were a
+rolled loop -- the one that held the IMAD.WIDE.U32 of the Payne-Hanek product; they are now the unrolled out-of-line
+routine dense_vector, one of the call targets, and the exact Payne-Hanek product another.)"""
 import collections
 import os
 import re
