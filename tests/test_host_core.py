@@ -126,6 +126,20 @@ def test_fast_large_argument_reduction_against_mpmath(fabe13):
         worst = max(worst, float(abs(mp.mpf(float(ri)) - true) / ulp))
     assert worst <= 0.501, worst
     assert ok.sum() >= 1490
+    # ... and where the fast form's absolute accuracy (~2^-74) weighs most: remainders just above its hand-over
+    # threshold, 2^-20 <= |r| < 2^-14 (a few hundred of 3e6 random arguments)
+    x = np.abs(_huge_from(rng, 3_000_000))
+    r, q, _, _, ok = _reduce_huge(fabe13, x)
+    near = (ok == 1) & (np.abs(r) < 2.0 ** -14)
+    assert 100 <= near.sum() <= 2000, near.sum()
+    worst = 0.0
+    for xi, ri, qi in zip(x[near], r[near], q[near]):
+        xm = mp.mpf(float(xi))
+        k = mp.nint(xm / pio2)
+        assert int(k) % 4 == qi, xi
+        ulp = 2.0 ** (np.frexp(ri)[1] - 53)
+        worst = max(worst, float(abs(mp.mpf(float(ri)) - (xm - k * pio2)) / ulp))
+    assert worst <= 0.75, worst
 
 
 def test_ph_remainder_table_is_what_the_generator_produces(tmp_path):
