@@ -240,6 +240,12 @@ void host_sincosf_array(const float* in, float* sin_out, float* cos_out, size_t 
 void host_reduce_huge(const double* in, double* r, int* q, double* r_exact, int* q_exact, int* fast_ok, size_t n) {
     for (size_t i = 0; i < n; ++i) {
         const uint64_t xb = fabe13_bits(in[i]);
+        if (!fabe13_is_huge(fabe13_abs_hi(xb))) {  // not an argument of this reduction (the table starts at 2^45): say so
+            r[i] = r_exact[i] = fabe13_from_bits(FABE13_QNAN_BITS);
+            q[i] = q_exact[i] = -1;
+            fast_ok[i] = 0;
+            continue;
+        }
         uint32_t qq;
         r[i] = fabe13_payne_hanek(xb, h_ph_stream, &qq);
         q[i] = (int)qq;

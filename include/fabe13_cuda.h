@@ -169,7 +169,7 @@ void fabe13_debug_host_array(const double* in, double* sin_out, double* cos_out,
 void fabe13_debug_host_array_stores(const double* in, double* sin_out, double* cos_out, size_t n, int op, int core, int threads,
                                     int stream_stores);
 
-/* The reduction of large arguments (2^45 <= |x| < Inf; every in[i] must be in that range) on the host: r[i] and
+/* The reduction of large arguments (2^45 <= |x| < Inf; any other in[i] gets r = NaN, q = -1, fast_ok = 0) on the host: r[i] and
  * q[i] = rint(x 2/pi) mod 4 as the product computes them (the fast form: tabulated remainders of the powers of two modulo
  * 2 pi, then Cody-Waite; the exact 192-bit form where the fast one hands over), r_exact / q_exact from the exact form
  * alone, fast_ok[i] = 1 where the fast form vouched for its own result. */

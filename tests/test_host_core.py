@@ -105,6 +105,9 @@ def test_fast_large_argument_reduction_hands_over_where_it_must(fabe13):
     assert not ok.any()
     assert np.array_equal(bits(r), bits(re)) and np.array_equal(q, qe)
     assert np.all(np.abs(r[:6]) < 2.0 ** -20) and np.all(np.abs(r[6:12]) > 0.78539434) and abs(r[12]) < 2.0 ** -60
+    # arguments outside the reduction's range are refused, not looked up
+    r, q, re, qe, ok = _reduce_huge(fabe13, np.array([1.0, -3.0e13, 0.0, np.inf, np.nan, 5e-324]))
+    assert np.all(np.isnan(r)) and np.all(np.isnan(re)) and np.all(q == -1) and np.all(qe == -1) and not ok.any()
 
 
 def test_fast_large_argument_reduction_against_mpmath(fabe13):
